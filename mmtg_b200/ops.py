@@ -1,0 +1,64 @@
+"""Thin Python wrappers over the C-ABI ops (raw pointers + current stream)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_NEW, ACT_NONE, ACT_TANH, BF16, F32  # noqa: F401
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "matrix must be row-major with unit inner stride"
+    return t.stride(0)
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
+         a_mn_major: bool = False, b_mn_major: bool = False, bias=None, act: int = ACT_NONE,
+         out2=None, residual=None, dgelu_src=None, rowtab0=None, rowidx0=None, rowmod0: int = 0,
+         rowtab1=None, rowidx1=None, colsum=None, lse_partial=None, accumulate: bool = False,
+         split_k: int = 1, block_n: int = 0) -> torch.Tensor:
+    """out = epilogue(A · Bᵀ) on the tcgen05 GEMM (see include/mmtg_b200.h: mmtg_gemm_bf16)."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    assert out.dtype in (torch.float32, torch.bfloat16)
+    a = _lib.GemmArgs()
+    a.A, a.B = A.data_ptr(), B.data_ptr()
+    a.lda, a.ldb = _ld(A), _ld(B)
+    a.a_mn_major, a.b_mn_major = int(a_mn_major), int(b_mn_major)
+    a.M, a.N, a.K = M, N, K
+    a.split_k, a.block_n = split_k, block_n
+    a.out, a.ldo = out.data_ptr(), _ld(out)
+    a.out_dtype = F32 if out.dtype == torch.float32 else BF16
+    a.accumulate = int(accumulate)
+    if out2 is not None:
+        assert out2.dtype == torch.bfloat16
+        a.out2, a.ldo2 = out2.data_ptr(), _ld(out2)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+        a.bias = bias.data_ptr()
+    a.act = act
+    if residual is not None:
+        assert residual.dtype == torch.float32
+        a.residual, a.ldr = residual.data_ptr(), _ld(residual)
+    if dgelu_src is not None:
+        assert dgelu_src.dtype == torch.bfloat16
+        a.dgelu_src, a.ldg = dgelu_src.data_ptr(), _ld(dgelu_src)
+    if rowtab0 is not None:
+        assert rowtab0.dtype == torch.float32
+        a.rowtab0, a.ldt0 = rowtab0.data_ptr(), _ld(rowtab0)
+        if rowidx0 is not None:
+            assert rowidx0.dtype == torch.int32
+            a.rowidx0 = rowidx0.data_ptr()
+        a.rowmod0 = rowmod0
+    if rowtab1 is not None:
+        assert rowtab1.dtype == torch.float32 and rowidx1.dtype == torch.int32
+        a.rowtab1, a.ldt1, a.rowidx1 = rowtab1.data_ptr(), _ld(rowtab1), rowidx1.data_ptr()
+    if colsum is not None:
+        assert colsum.dtype == torch.float32
+        a.colsum = colsum.data_ptr()
+    if lse_partial is not None:
+        assert lse_partial.dtype == torch.float32
+        a.lse_partial = lse_partial.data_ptr()
+    _lib.check(_lib.lib().mmtg_gemm_bf16(C.byref(a), C.c_void_p(_lib.stream_ptr())), "mmtg_gemm_bf16")
+    return out

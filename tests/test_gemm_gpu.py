@@ -1,0 +1,116 @@
+"""tcgen05 GEMM parity vs a plain PyTorch fp32 reference of the same contraction (bf16 inputs,
+fp32 accumulate). Tolerance: fp32 outputs |Δ| ≤ 2e-3·sqrt(K/64) absolute on unit-variance data
+(accumulation-order differences only); bf16 outputs additionally 1 bf16 ulp (rtol 8e-3)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, cols, mn_major, gen, dev):
+    """Logical [rows, cols(K)] operand; stored transposed when mn_major."""
+    x = torch.randn(rows, cols, generator=gen, device=dev).to(torch.bfloat16)
+    stored = x.t().contiguous() if mn_major else x
+    return x, stored
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (472, 768, 768),
+                                   (7552, 768, 768), (300, 520, 200), (160, 1536, 2048)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_plain(cuda, M, N, K, a_mn, b_mn, bn):
+    from mmtg_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(M * 7 + N * 3 + K)
+    # MN-major storage needs pitches that are multiples of 8 elements
+    if (a_mn and M % 8) or (b_mn and N % 8) or K % 8:
+        pytest.skip("pitch not TMA-aligned for this layout")
+    A, As = _mk(M, K, a_mn, g, cuda)
+    B, Bs = _mk(N, K, b_mn, g, cuda)
+    out = torch.full((M, N), float("nan"), device=cuda)
+    ops.gemm(As, Bs, out, M=M, N=N, K=K, a_mn_major=a_mn, b_mn_major=b_mn, block_n=bn)
+    ref = A.float() @ B.float().t()
+    torch.cuda.synchronize()
+    tol = 2e-3 * math.sqrt(max(K, 64) / 64)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= tol, (out - ref).abs().max().item()
+
+
+def test_gemm_epilogues(cuda):
+    from mmtg_b200 import ops
+    M, N, K = 472, 768, 512
+    g = torch.Generator(device=cuda).manual_seed(1)
+    A = (torch.randn(M, K, generator=g, device=cuda) * 0.5).to(torch.bfloat16)
+    B = (torch.randn(N, K, generator=g, device=cuda) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device=cuda)
+    res = torch.randn(M, N, generator=g, device=cuda)
+    base = A.float() @ B.float().t() + bias
+    # bias + gelu_new, bf16 out + pre-activation copy + colsum
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    cs = torch.zeros(N, device=cuda)
+    ops.gemm(A, B, out, M=M, N=N, K=K, bias=bias, act=ops.ACT_GELU_NEW, out2=pre, colsum=cs)
+    ref = torch.nn.functional.gelu(base, approximate="tanh")
+    assert torch.allclose(out.float(), ref, atol=2e-3, rtol=8e-3)
+    assert torch.allclose(pre.float(), base, atol=2e-3, rtol=8e-3)
+    assert torch.allclose(cs, ref.sum(0), atol=0.05, rtol=1e-3)
+    # bias + tanh
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(A, B, out, M=M, N=N, K=K, bias=bias, act=ops.ACT_TANH)
+    assert torch.allclose(out.float(), torch.tanh(base), atol=2e-3, rtol=8e-3)
+    # bias + residual, fp32 out
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm(A, B, out, M=M, N=N, K=K, bias=bias, residual=res)
+    assert torch.allclose(out, base + res, atol=2e-3, rtol=1e-5)
+    # row-gather adds (wpe[row % L] + wte[type]) as in the projector epilogue
+    L = 236
+    tab0 = torch.randn(1024, N, generator=g, device=cuda)
+    tab1 = torch.randn(16, N, generator=g, device=cuda)
+    idx1 = torch.randint(0, 16, (M,), generator=g, device=cuda, dtype=torch.int32)
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm(A, B, out, M=M, N=N, K=K, bias=bias, rowtab0=tab0, rowmod0=L, rowtab1=tab1, rowidx1=idx1)
+    rows = torch.arange(M, device=cuda)
+    ref = base + tab0[rows % L] + tab1[idx1.long()]
+    assert torch.allclose(out, ref, atol=2e-3, rtol=1e-5)
+    # dgelu multiply
+    u = torch.randn(M, N, generator=g, device=cuda).to(torch.bfloat16)
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(A, B, out, M=M, N=N, K=K, dgelu_src=u)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf, approximate="tanh").sum().backward()
+    ref = (A.float() @ B.float().t()) * uf.grad
+    assert torch.allclose(out.float(), ref, atol=3e-3, rtol=8e-3)
+
+
+@pytest.mark.parametrize("split", [2, 4, 7])
+def test_gemm_wgrad_splitk(cuda, split):
+    """wgrad shape: dW[768,2304] += Xᵀ[768,M] · dY[M,2304] with both operands MN-major."""
+    from mmtg_b200 import ops
+    M, Kin, Nout = 1416, 768, 2304
+    g = torch.Generator(device=cuda).manual_seed(2)
+    X = torch.randn(M, Kin, generator=g, device=cuda).to(torch.bfloat16)
+    dY = (torch.randn(M, Nout, generator=g, device=cuda) * 0.1).to(torch.bfloat16)
+    acc = torch.ones(Kin, Nout, device=cuda)
+    ops.gemm(X, dY, acc, M=Kin, N=Nout, K=M, a_mn_major=True, b_mn_major=True, split_k=split)
+    ref = 1.0 + X.float().t() @ dY.float()
+    assert (acc - ref).abs().max().item() <= 2e-2
+
+
+def test_gemm_lmhead_odd_pitch_and_lse(cuda):
+    """lm_head: N = 13317 (odd pitch, fp32 contiguous logits) + fused per-row LSE partials."""
+    from mmtg_b200 import ops
+    M, N, K = 472, 13317, 768
+    g = torch.Generator(device=cuda).manual_seed(3)
+    H = torch.randn(M, K, generator=g, device=cuda).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device=cuda) * 0.02).to(torch.bfloat16)
+    for bn in (128, 256):
+        out = torch.empty(M, N, device=cuda)
+        nt = (N + bn - 1) // bn
+        part = torch.empty(nt, M, 2, device=cuda)
+        ops.gemm(H, W, out, M=M, N=N, K=K, lse_partial=part, block_n=bn)
+        ref = H.float() @ W.float().t()
+        assert (out - ref).abs().max().item() <= 5e-3
+        mx = part[..., 0].max(0).values
+        lse = mx + torch.log((part[..., 1] * torch.exp(part[..., 0] - mx)).sum(0))
+        assert torch.allclose(lse, torch.logsumexp(ref, -1), atol=1e-3, rtol=1e-5)
