@@ -83,9 +83,136 @@ typedef struct mmtg_gemm_args {
   /* optional per-row (max, sum-exp) partials of the stored value over this tile's columns,
    * layout [ceil(N/block_n)][M][2] fp32 — lets the loss kernels skip a full re-read of logits */
   float* lse_partial;
+  /* 0: dgelu_src holds the pre-activation u, value *= gelu_new'(u);
+   * 1: dgelu_src holds a tanh OUTPUT y, value *= (1 - y*y)   (projector backward) */
+  int32_t dact_tanh_out;
+  int32_t _pad2;
 } mmtg_gemm_args;
 
 int mmtg_gemm_bf16(const mmtg_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound). Reference call sites in each comment.
+ * ------------------------------------------------------------------------------------------ */
+/* torch.nn.LayerNorm fwd (src/model.py:380-382; HF GPT2Block ln_1/ln_2, GPT2Model ln_f). E in {512,768} */
+int mmtg_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                       float* y_f32, float* mean, float* rstd, int32_t M, int32_t E, float eps,
+                       void* stream);
+/* its autograd backward; dx written or accumulated; dgamma/dbeta accumulated (atomics) */
+int mmtg_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const float* x, const float* mean,
+                       const float* rstd, const float* gamma, float* dx, int32_t accumulate_dx,
+                       float* dgamma, float* dbeta, int32_t M, int32_t E, void* stream);
+int mmtg_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* bias gradients: out[N] += column sums of x[M,N]; optional bf16 copy of an fp32 x */
+int mmtg_colsum(const void* x, int32_t x_is_bf16, int64_t ld, void* copy_bf16, int64_t ldc,
+                float* out, int32_t M, int32_t N, void* stream);
+/* GPT2_Decoder embedding build, src/model.py:253-277 (token->WenLan gather + context add) */
+int mmtg_embed_fwd(const float* table, const int32_t* topic_ids, const int32_t* input_ids,
+                   const float* ctx, void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t S,
+                   int32_t two_sent, int32_t D, void* stream);
+int mmtg_embed_bwd(const void* dE_bf16, void* dctx_bf16, float* dctx_f32, int32_t B, int32_t P,
+                   int32_t T, int32_t S, int32_t two_sent, int32_t D, void* stream);
+
+/* HF GPT2Attention (modeling_gpt2.py:54-72): causal + key-padding softmax(QK^T/8)V, head_dim 64.
+ * qkv [B*L, 3E] bf16; out [B*L, E] bf16; lse [B, n_head, L] fp32. */
+int mmtg_attn_fwd(const void* qkv, const int32_t* key_mask, void* out, float* lse, int32_t B,
+                  int32_t L, int32_t n_head, void* stream);
+int mmtg_attn_bwd(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,
+                  const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L,
+                  int32_t n_head, void* stream);
+
+/* Loss reductions: HF ForCausalLMLoss (loss/loss_utils.py:28-67) and MyLoss (src/loss.py:45-74) */
+int mmtg_lse_rows(const float* logits, int64_t ld, float* lse, int32_t M, int32_t V, void* stream);
+int mmtg_lse_combine(const float* partials, float* lse, int32_t M, int32_t ntiles, void* stream);
+int mmtg_ce_reduce(const float* logits, int64_t ld, const float* lse, const int32_t* topic_ids,
+                   const int32_t* targets, float* hf_sum_ws, float* ce, float* hf_loss, int32_t B,
+                   int32_t L, int32_t P, int32_t T, void* stream);
+int mmtg_negloss(const float* ce, const int32_t* ratings, int32_t stage, float* loss, float* coef,
+                 int32_t B, void* stream);
+int mmtg_ce_bwd(const float* logits, int64_t ld, const float* lse, const int32_t* topic_ids,
+                const int32_t* targets, const float* coef, const float* g_my, const float* g_hf,
+                void* out, int32_t out_is_bf16, int64_t ldo, int32_t B, int32_t L, int32_t P,
+                int32_t T, int32_t V, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-path engine: MMTG.forward (src/model.py:356-400, training branch) and its backward,
+ * orchestrated natively on one stream. All parameters live in ONE flat fp32 buffer (plus a
+ * bf16 shadow for GEMM operands and a flat fp32 gradient buffer) addressed by element offsets.
+ * ------------------------------------------------------------------------------------------ */
+#define MMTG_MAX_LAYERS 48
+
+typedef struct mmtg_dims {
+  int32_t B, P, T, L;          /* L = P + T */
+  int32_t S, two_sent;         /* experience steps (5); tokens per sentence pair (44) */
+  int32_t Dw, He, alpha_heads; /* 2048, 512, 4 */
+  int32_t E, NH, NL, V, Vp;    /* 768, 12, 12, 13317, V rounded up to a multiple of 8 */
+  int32_t n_pos, _pad;
+} mmtg_dims;
+
+typedef struct mmtg_layer_offsets {
+  int64_t ln1_w, ln1_b, attn_w, attn_b, proj_w, proj_b, ln2_w, ln2_b, fc_w, fc_b, proj2_w, proj2_b;
+} mmtg_layer_offsets;
+
+typedef struct mmtg_param_offsets {
+  int64_t topic_w, topic_b;
+  int64_t gru_w_ih[2], gru_w_hh[2], gru_b_ih[2], gru_b_hh[2]; /* 0 = image, 1 = text */
+  int64_t enc_ln_w[3], enc_ln_b[3];                           /* topic, image, text */
+  int64_t alpha_qkv_w[2], alpha_qkv_b[2];                     /* q|k|v stacked: [3He,He], [3He] */
+  int64_t beta_att_w, beta_att_b;                             /* [S,He], [S] */
+  int64_t beta_out_w, beta_out_b;
+  int64_t proj1_w, proj1_b, proj2_w, proj2_b;
+  int64_t wte, wpe;
+  int64_t lnf_w, lnf_b;
+  mmtg_layer_offsets layer[MMTG_MAX_LAYERS];
+} mmtg_param_offsets;
+
+typedef struct mmtg_model {
+  mmtg_dims dims;
+  mmtg_param_offsets off;
+  const float* params;      /* flat fp32 master weights */
+  const void* params_bf16;  /* flat bf16 shadow (same offsets) */
+  float* grads;             /* flat fp32 gradients (same offsets), accumulated into */
+  const float* token_table; /* [V, Dw] fp32, frozen (vocab/token_id2emb_dict.pkl) */
+} mmtg_model;
+
+typedef struct mmtg_batch {
+  const int32_t* topic_ids; /* [B,P] */
+  const int32_t* targets;   /* [B,T] */
+  const int32_t* type_ids;  /* [B,L] = cat(tpw_type_ids, type_ids) */
+  const int32_t* attn_mask; /* [B,L] = cat(tpw_attention_mask, attention_mask) */
+  const float* topic_emb;   /* [B,Dw] */
+  const float* img_embs;    /* [B,S,Dw] */
+  const float* txt_embs;    /* [B,S,Dw] */
+} mmtg_batch;
+
+int64_t mmtg_train_workspace_bytes(const mmtg_dims* dims);
+/* scalars_out: [0] = HF causal-LM loss, [1] = KL regulariser. logits: [B,L,V] fp32 contiguous. */
+int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
+                       int64_t workspace_bytes, float* logits, float* scalars_out, int32_t save_for_backward,
+                       void* stream);
+/* device pointers into the workspace that the loss path reads/writes */
+float* mmtg_ws_lse(const mmtg_dims* dims, void* workspace);          /* [B*L] row log-sum-exp */
+void* mmtg_ws_dlogits_bf16(const mmtg_dims* dims, void* workspace);  /* [B*L, Vp] bf16 */
+/* Backward stages: 0 = lm_head + ln_f, 1..NL = blocks NL-1..0, NL+1 = projector/embedding/encoder.
+ * Runs stages [stage_begin, stage_end). dlogits come from mmtg_ws_dlogits_bf16 (write them, or
+ * convert an fp32 [B*L, V] gradient with mmtg_dlogits_from_f32, before stage 0).
+ * g_kl: device scalar d(total)/d(kl) or null (= 0). */
+int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
+                        int64_t workspace_bytes, const float* g_kl, int32_t stage_begin,
+                        int32_t stage_end, void* stream);
+int mmtg_dlogits_from_f32(const mmtg_dims* dims, void* workspace, const float* dlogits_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step over the flat buffers: clip_grad_norm_ (src/train.py:194) and
+ * transformers.AdamW as the reference configures it (src/train.py:137: eps 1e-6 outside the
+ * bias-corrected denominator, decoupled weight decay 0), refreshing the bf16 shadow in-pass.
+ * ------------------------------------------------------------------------------------------ */
+int mmtg_grad_norm_sq(const float* grads, int64_t n, float* partial_ws, int32_t partial_len,
+                      float* out_normsq, void* stream);
+int mmtg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    void* params_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int32_t step, int32_t correct_bias, const float* normsq,
+                    float max_norm, void* stream);
 
 #ifdef __cplusplus
 }

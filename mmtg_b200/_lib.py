@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("rowtab1", C.c_void_p), ("rowidx1", C.c_void_p), ("ldt1", C.c_int64),
         ("colsum", C.c_void_p),
         ("lse_partial", C.c_void_p),
+        ("dact_tanh_out", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -55,6 +56,9 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.mmtg_last_error.restype = C.c_char_p
         _lib.mmtg_launch_count.restype = C.c_int64
+        _lib.mmtg_train_workspace_bytes.restype = C.c_int64
+        _lib.mmtg_ws_lse.restype = C.c_void_p
+        _lib.mmtg_ws_dlogits_bf16.restype = C.c_void_p
         if _lib.mmtg_abi_version() != 1:
             raise MMTGError("libmmtg_b200.so ABI version mismatch")
     return _lib

@@ -1,0 +1,558 @@
+// Fused causal + key-padding softmax attention for the GPT-2 decoder (head_dim 64), forward and
+// backward. Replaces HF GPT2Attention's SDPA call (transformers modeling_gpt2.py:54-72,144-226)
+// and its autograd backward.
+//
+// Layout: qkv is the c_attn output [B*L, 3*E] bf16 (q | k | v, heads contiguous 64-wide slices);
+// out is [B*L, E] bf16 with heads merged — exactly what c_proj consumes, so no permutes exist.
+// Flash-style: 64-query x 64-key tiles, online softmax in the exp2 domain, K/V (fwd) or Q/dO
+// (bwd) tiles double-buffered in shared memory with cp.async, XOR-swizzled 16-byte chunks so
+// ldmatrix is conflict-free. Tensor-core math is mma.sync m16n8k16 bf16 (legacy HMMA path):
+// attention is 2 % of the step's FLOPs; the tcgen05 version is tracked in DESIGN.md.
+#include "../../include/mmtg_b200.h"
+#include "common.cuh"
+
+namespace mmtg {
+
+namespace {
+
+constexpr int HD = 64;       // head dim
+constexpr int BQ = 64;       // query rows per CTA
+constexpr int BKV = 64;      // keys per tile
+constexpr int ATT_THREADS = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int sz = pred ? 16 : 0;  // zero-fill when out of range
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                          uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// A [64 rows][64 cols] bf16 tile in smem, 128 B per row, 16-B chunk c of row r stored at c^(r&7).
+__device__ __forceinline__ uint32_t tile_addr(const bf16* tile, int row, int chunk) {
+  return smem_u32(tile) + (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+// Load rows [row0, row0+64) x 64 columns (col0..col0+63) of a [*, ld] bf16 matrix; rows >= nrows
+// are zero-filled. 128 threads, 4 x 16-B chunks each.
+__device__ __forceinline__ void load_tile_async(bf16* tile, const bf16* g, long long ld, int row0,
+                                                int nrows_valid, int col0) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + i * ATT_THREADS;  // 0..511
+    const int r = idx >> 3, c = idx & 7;
+    const bool ok = (row0 + r) < nrows_valid;
+    const bf16* src = g + (long long)(ok ? (row0 + r) : 0) * ld + col0 + c * 8;
+    cp_async16(reinterpret_cast<uint8_t*>(tile) + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
+  }
+}
+
+// A-operand fragments (16 rows x 64 cols = 4 k-steps) of rows [row0, row0+16) of a tile.
+__device__ __forceinline__ void load_a_frags(const bf16* tile, int row0, uint32_t (&a)[4][4]) {
+  const int l = lane_id();
+  const int r = row0 + (l & 15), cg = l >> 4;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    ldsm_x4(tile_addr(tile, r, kk * 2 + cg), a[kk][0], a[kk][1], a[kk][2], a[kk][3]);
+}
+
+// C[16 x 64] += A_frags(16 x 64) * Tile^T where Tile is [64 n][64 k] (k contiguous): "NT".
+__device__ __forceinline__ void mma_nt(float (&c)[8][4], const uint32_t (&a)[4][4],
+                                       const bf16* tile) {
+  const int l = lane_id();
+#pragma unroll
+  for (int nb = 0; nb < 8; nb += 2) {
+    const int r = nb * 8 + (l & 7) + ((l >> 4) & 1) * 8;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(tile_addr(tile, r, kk * 2 + ((l >> 3) & 1)), b0, b1, b2, b3);
+      mma16816(c[nb], a[kk][0], a[kk][1], a[kk][2], a[kk][3], b0, b1);
+      mma16816(c[nb + 1], a[kk][0], a[kk][1], a[kk][2], a[kk][3], b2, b3);
+    }
+  }
+}
+// C[16 x 64] += P(16 x 64, fp32 C-fragments converted to bf16) * Tile where Tile is [64 k][64 n]
+// (n contiguous): "NN" via ldmatrix.trans.
+__device__ __forceinline__ void mma_nn(float (&c)[8][4], const float (&p)[8][4], const bf16* tile) {
+  const int l = lane_id();
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint32_t a0 = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
+    const uint32_t a1 = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+    const uint32_t a2 = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    const uint32_t a3 = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+    const int r = kk * 16 + (l & 7) + ((l >> 3) & 1) * 8;
+#pragma unroll
+    for (int nb = 0; nb < 8; nb += 2) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(tile_addr(tile, r, nb + (l >> 4)), b0, b1, b2, b3);
+      mma16816(c[nb], a0, a1, a2, a3, b0, b1);
+      mma16816(c[nb + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+}
+
+struct AttnParams {
+  const bf16* qkv;  // [B*L, 3E]
+  const int* kmask;  // [B, L] 1 = attend, 0 = padding key
+  bf16* out;        // [B*L, E]
+  float* lse;       // [B, NH, L] natural-log LSE of the scaled scores
+  const bf16* dout;  // [B*L, E]
+  const float* delta;  // [B, NH, L] rowsum(dO * O)
+  bf16* dqkv;       // [B*L, 3E]
+  int B, L, NH, E;
+  float scale;
+};
+
+// --------------------------------------------------------------------------------------------
+// forward
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(const AttnParams p) {
+  __shared__ __align__(128) bf16 sQ[BQ * HD];
+  __shared__ __align__(128) bf16 sK[2][BKV * HD];
+  __shared__ __align__(128) bf16 sV[2][BKV * HD];
+  __shared__ float sMask[2][BKV];
+
+  const int qb = (gridDim.x - 1) - blockIdx.x;  // heavy (late) query blocks first
+  const int bh = blockIdx.y;
+  const int b = bh / p.NH, h = bh - b * p.NH;
+  const int warp = threadIdx.x >> 5, l = lane_id();
+  const long long ld = 3LL * p.E;
+  const bf16* base = p.qkv + (long long)b * p.L * ld;
+  const int q0 = qb * BQ;
+
+  load_tile_async(sQ, base, ld, q0, p.L, h * HD);
+  const int nkv = qb + 1;  // causal: key tiles 0..qb
+  auto issue_kv = [&](int t, int buf) {
+    load_tile_async(sK[buf], base, ld, t * BKV, p.L, p.E + h * HD);
+    load_tile_async(sV[buf], base, ld, t * BKV, p.L, 2 * p.E + h * HD);
+    if (threadIdx.x < BKV) {
+      const int key = t * BKV + threadIdx.x;
+      const bool ok = key < p.L && (p.kmask == nullptr || p.kmask[b * p.L + key] != 0);
+      sMask[buf][threadIdx.x] = ok ? 0.f : -INFINITY;
+    }
+  };
+  issue_kv(0, 0);
+  cp_async_commit();
+
+  const float sl2 = p.scale * LOG2E;
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qa[4][4];
+  const int row_lo = q0 + warp * 16 + (l >> 2);  // this thread's rows: row_lo, row_lo + 8
+
+  for (int t = 0; t < nkv; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nkv) issue_kv(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (t == 0) load_a_frags(sQ, warp * 16, qa);
+
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    mma_nt(s, qa, sK[buf]);
+
+    // mask + online softmax (exp2 domain)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kc = nb * 8 + (l & 3) * 2 + (j & 1);
+        const int key = t * BKV + kc;
+        const int row = row_lo + (j >> 1) * 8;
+        float v = s[nb][j] * sl2 + sMask[buf][kc];
+        if (key > row) v = -INFINITY;
+        s[nb][j] = v;
+        mx[j >> 1] = fmaxf(mx[j >> 1], v);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mnew[r] = fmaxf(m_run[r], mx[r]);
+      const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+      corr[r] = exp2f(m_run[r] - msafe);  // m_run = -inf -> 0
+      m_run[r] = mnew[r];
+      mnew[r] = msafe;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float e = exp2f(s[nb][j] - mnew[j >> 1]);
+        s[nb][j] = e;
+        rs[j >> 1] += e;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      o[nb][0] *= corr[0]; o[nb][1] *= corr[0];
+      o[nb][2] *= corr[1]; o[nb][3] *= corr[1];
+    }
+    mma_nn(o, s, sV[buf]);
+    __syncthreads();  // all warps done with buf before it is refilled next iteration
+  }
+
+  // finalize: O /= l, write bf16; LSE = (m + log2(l)) / log2(e)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row_lo + r * 8;
+    if (row < p.L) {
+      const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+      bf16* dst = p.out + ((long long)b * p.L + row) * p.E + h * HD + (l & 3) * 2;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+        *reinterpret_cast<uint32_t*>(dst + nb * 8) =
+            pack_bf16(o[nb][2 * r] * inv, o[nb][2 * r + 1] * inv);
+      if ((l & 3) == 0 && p.lse)
+        p.lse[((long long)b * p.NH + h) * p.L + row] =
+            l_run[r] > 0.f ? (m_run[r] + log2f(l_run[r])) / LOG2E : -INFINITY;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// backward preprocess: delta[b,h,q] = sum_d dO[q,d] * O[q,d]
+// --------------------------------------------------------------------------------------------
+__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                                  float* __restrict__ delta, int B, int L, int NH, int E) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int l = lane_id();
+  const long long total = (long long)B * L * NH;
+  if (gw >= total) return;
+  const int h = (int)(gw % NH);
+  const long long row = gw / NH;  // b*L + q
+  const long long off = row * E + h * HD + l * 2;
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + off));
+  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
+  const float s = warp_sum(a.x * d.x + a.y * d.y);
+  if (l == 0) {
+    const int b = (int)(row / L), q = (int)(row - (long long)b * L);
+    delta[((long long)b * NH + h) * L + q] = s;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// backward, dK/dV: one CTA per (key tile, b, h); loops over query tiles >= key tile.
+// Works on transposed tiles (rows = keys) so both outputs accumulate in registers.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dkdv_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  bf16* sK = reinterpret_cast<bf16*>(att_smem);
+  bf16* sV = sK + BKV * HD;
+  bf16(*sQ)[BQ * HD] = reinterpret_cast<bf16(*)[BQ * HD]>(sV + BKV * HD);
+  bf16(*sdO)[BQ * HD] = reinterpret_cast<bf16(*)[BQ * HD]>(sV + BKV * HD + 2 * BQ * HD);
+  float(*sLse)[BQ] = reinterpret_cast<float(*)[BQ]>(sV + BKV * HD + 4 * BQ * HD);
+  float(*sDelta)[BQ] = sLse + 2;
+
+  const int kb = blockIdx.x;
+  const int bh = blockIdx.y;
+  const int b = bh / p.NH, h = bh - b * p.NH;
+  const int warp = threadIdx.x >> 5, l = lane_id();
+  const long long ld = 3LL * p.E;
+  const bf16* base = p.qkv + (long long)b * p.L * ld;
+  const bf16* dobase = p.dout + (long long)b * p.L * p.E;
+  const int k0 = kb * BKV;
+  const int nq = (p.L + BQ - 1) / BQ;
+
+  load_tile_async(sK, base, ld, k0, p.L, p.E + h * HD);
+  load_tile_async(sV, base, ld, k0, p.L, 2 * p.E + h * HD);
+  auto issue_q = [&](int t, int buf) {
+    load_tile_async(sQ[buf], base, ld, t * BQ, p.L, h * HD);
+    load_tile_async(sdO[buf], dobase, p.E, t * BQ, p.L, h * HD);
+    if (threadIdx.x < BQ) {
+      const int q = t * BQ + threadIdx.x;
+      const long long o = ((long long)b * p.NH + h) * p.L + q;
+      const float lv = q < p.L ? p.lse[o] : -INFINITY;
+      sLse[buf][threadIdx.x] = lv == -INFINITY ? INFINITY : lv * LOG2E;  // +inf -> P = 0
+      sDelta[buf][threadIdx.x] = q < p.L ? p.delta[o] : 0.f;
+    }
+  };
+  issue_q(kb, 0);
+  cp_async_commit();
+
+  const float sl2 = p.scale * LOG2E;
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
+  uint32_t ka[4][4], va[4][4];
+  const int key_lo = k0 + warp * 16 + (l >> 2);
+  bool keyok[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = key_lo + r * 8;
+    keyok[r] = key < p.L && (p.kmask == nullptr || p.kmask[b * p.L + key] != 0);
+  }
+
+  for (int t = kb; t < nq; ++t) {
+    const int buf = (t - kb) & 1;
+    if (t + 1 < nq) issue_q(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (t == kb) {
+      load_a_frags(sK, warp * 16, ka);
+      load_a_frags(sV, warp * 16, va);
+    }
+    // S^T = K Q^T  (rows = keys, cols = queries)
+    float st[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st[i][j] = 0.f;
+    mma_nt(st, ka, sQ[buf]);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qc = nb * 8 + (l & 3) * 2 + (j & 1);
+        const int q = t * BQ + qc;
+        const int key = key_lo + (j >> 1) * 8;
+        const bool ok = keyok[j >> 1] && key <= q;
+        st[nb][j] = ok ? exp2f(st[nb][j] * sl2 - sLse[buf][qc]) : 0.f;  // P^T
+      }
+    }
+    mma_nn(dv, st, sdO[buf]);  // dV += P^T dO
+    // dP^T = V dO^T
+    float dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dpt[i][j] = 0.f;
+    mma_nt(dpt, va, sdO[buf]);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qc = nb * 8 + (l & 3) * 2 + (j & 1);
+        dpt[nb][j] = st[nb][j] * (dpt[nb][j] - sDelta[buf][qc]);  // dS^T
+      }
+    }
+    mma_nn(dk, dpt, sQ[buf]);  // dK += dS^T Q
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = key_lo + r * 8;
+    if (key < p.L) {
+      bf16* dst = p.dqkv + ((long long)b * p.L + key) * ld + h * HD + (l & 3) * 2;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        *reinterpret_cast<uint32_t*>(dst + p.E + nb * 8) =
+            pack_bf16(dk[nb][2 * r] * p.scale, dk[nb][2 * r + 1] * p.scale);
+        *reinterpret_cast<uint32_t*>(dst + 2 * p.E + nb * 8) =
+            pack_bf16(dv[nb][2 * r], dv[nb][2 * r + 1]);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// backward, dQ: one CTA per (query tile, b, h); loops over key tiles <= query tile.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dq_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(att_smem);
+  bf16* sdO = sQ + BQ * HD;
+  bf16(*sK)[BKV * HD] = reinterpret_cast<bf16(*)[BKV * HD]>(sdO + BQ * HD);
+  bf16(*sV)[BKV * HD] = reinterpret_cast<bf16(*)[BKV * HD]>(sdO + BQ * HD + 2 * BKV * HD);
+  float(*sMask)[BKV] = reinterpret_cast<float(*)[BKV]>(sdO + BQ * HD + 4 * BKV * HD);
+
+  const int qb = (gridDim.x - 1) - blockIdx.x;
+  const int bh = blockIdx.y;
+  const int b = bh / p.NH, h = bh - b * p.NH;
+  const int warp = threadIdx.x >> 5, l = lane_id();
+  const long long ld = 3LL * p.E;
+  const bf16* base = p.qkv + (long long)b * p.L * ld;
+  const bf16* dobase = p.dout + (long long)b * p.L * p.E;
+  const int q0 = qb * BQ;
+
+  load_tile_async(sQ, base, ld, q0, p.L, h * HD);
+  load_tile_async(sdO, dobase, p.E, q0, p.L, h * HD);
+  const int nkv = qb + 1;
+  auto issue_kv = [&](int t, int buf) {
+    load_tile_async(sK[buf], base, ld, t * BKV, p.L, p.E + h * HD);
+    load_tile_async(sV[buf], base, ld, t * BKV, p.L, 2 * p.E + h * HD);
+    if (threadIdx.x < BKV) {
+      const int key = t * BKV + threadIdx.x;
+      const bool ok = key < p.L && (p.kmask == nullptr || p.kmask[b * p.L + key] != 0);
+      sMask[buf][threadIdx.x] = ok ? 0.f : -INFINITY;
+    }
+  };
+  issue_kv(0, 0);
+  cp_async_commit();
+
+  const float sl2 = p.scale * LOG2E;
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+  uint32_t qa[4][4], doa[4][4];
+  const int row_lo = q0 + warp * 16 + (l >> 2);
+  float lse2[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row_lo + r * 8;
+    const long long o = ((long long)b * p.NH + h) * p.L + row;
+    const float lv = row < p.L ? p.lse[o] : -INFINITY;
+    lse2[r] = lv == -INFINITY ? INFINITY : lv * LOG2E;
+    dl[r] = row < p.L ? p.delta[o] : 0.f;
+  }
+
+  for (int t = 0; t < nkv; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nkv) issue_kv(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (t == 0) {
+      load_a_frags(sQ, warp * 16, qa);
+      load_a_frags(sdO, warp * 16, doa);
+    }
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.f;
+    mma_nt(s, qa, sK[buf]);
+    mma_nt(dp, doa, sV[buf]);  // dP = dO V^T
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kc = nb * 8 + (l & 3) * 2 + (j & 1);
+        const int key = t * BKV + kc;
+        const int row = row_lo + (j >> 1) * 8;
+        const float pv = (key <= row && sMask[buf][kc] == 0.f)
+                             ? exp2f(s[nb][j] * sl2 - lse2[j >> 1]) : 0.f;
+        s[nb][j] = pv * (dp[nb][j] - dl[j >> 1]);  // dS
+      }
+    }
+    mma_nn(dq, s, sK[buf]);  // dQ += dS K
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row_lo + r * 8;
+    if (row < p.L) {
+      bf16* dst = p.dqkv + ((long long)b * p.L + row) * ld + h * HD + (l & 3) * 2;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+        *reinterpret_cast<uint32_t*>(dst + nb * 8) =
+            pack_bf16(dq[nb][2 * r] * p.scale, dq[nb][2 * r + 1] * p.scale);
+    }
+  }
+}
+
+}  // namespace
+
+void count_launch(int n = 1);
+
+int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
+             cudaStream_t st) {
+  AttnParams p{};
+  p.qkv = qkv; p.kmask = kmask; p.out = out; p.lse = lse;
+  p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
+  dim3 grid(cdiv(L, BQ), B * NH);
+  attn_fwd_kernel<<<grid, ATT_THREADS, 0, st>>>(p);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
+             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st) {
+  AttnParams p{};
+  p.qkv = qkv; p.kmask = kmask; p.lse = const_cast<float*>(lse); p.dout = dout; p.delta = delta;
+  p.dqkv = dqkv; p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
+  const long long warps = (long long)B * L * NH;
+  attn_delta_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, st>>>(out, dout, delta, B, L, NH, p.E);
+  MMTG_LAUNCH_OK();
+  dim3 grid(cdiv(L, BQ), B * NH);
+  constexpr int BWD_SMEM = 6 * BQ * HD * 2 + 4 * BQ * 4;  // 6 bf16 tiles + 4 x 64 floats
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr_set = true;
+  }
+  attn_bwd_dkdv_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(p);
+  MMTG_LAUNCH_OK();
+  attn_bwd_dq_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(p);
+  MMTG_LAUNCH_OK();
+  count_launch(3);
+  return 0;
+}
+
+}  // namespace mmtg
+
+using namespace mmtg;
+
+extern "C" int mmtg_attn_fwd(const void* qkv, const int32_t* key_mask, void* out, float* lse,
+                             int32_t B, int32_t L, int32_t n_head, void* stream) {
+  MMTG_CHECK_ARG(qkv && out && B > 0 && L > 0 && n_head > 0, "bad attention args");
+  return attn_fwd((const bf16*)qkv, key_mask, (bf16*)out, lse, B, L, n_head, (cudaStream_t)stream);
+}
+
+extern "C" int mmtg_attn_bwd(const void* qkv, const int32_t* key_mask, const void* out,
+                             const void* dout, const float* lse, float* delta_ws, void* dqkv,
+                             int32_t B, int32_t L, int32_t n_head, void* stream) {
+  MMTG_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && L > 0 && n_head > 0,
+                 "bad attention bwd args");
+  return attn_bwd((const bf16*)qkv, key_mask, (const bf16*)out, (const bf16*)dout, lse, delta_ws,
+                  (bf16*)dqkv, B, L, n_head, (cudaStream_t)stream);
+}

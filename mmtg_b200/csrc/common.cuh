@@ -54,7 +54,7 @@ const char* get_last_error();
 
 int num_sms();  // cached SM count of the current device
 
-static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__

@@ -1,0 +1,451 @@
+// HBM-bound row kernels of the MMTG hot path: LayerNorm fwd/bwd, fp32->bf16 casts, column sums
+// (bias gradients), and the decoder embedding build (token -> WenLan gather + fused-context add)
+// with its backward. Every kernel is vectorised and coalesced; grids are sized in multiples of
+// the SM count where the loop is grid-strided.
+//
+// Replaces: torch LayerNorm (src/model.py:380-382, HF GPT2Block ln_1/ln_2/ln_f), the Python
+// per-token embedding loops of GPT2_Decoder.forward (src/model.py:253-268) and the ATen
+// reductions autograd uses for bias gradients.
+#include "../../include/mmtg_b200.h"
+#include "common.cuh"
+
+namespace mmtg {
+
+void count_launch(int n = 1);
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, row kept in registers (two-pass mean / variance).
+// ------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, bf16* __restrict__ y16, float* __restrict__ y32,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, float eps) {
+  constexpr int V = E / 128;  // float4 per lane
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int l = lane_id();
+  for (int row = warp; row < M; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * E);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = __ldg(xr + l + i * 32);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) * (1.f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / E) + eps);
+    if (l == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c4 = l + i * 32;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y32) reinterpret_cast<float4*>(y32 + (long long)row * E)[c4] = o;
+      if (y16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        reinterpret_cast<uint2*>(y16 + (long long)row * E)[c4] =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.
+// dx is written or accumulated (residual-stream gradient); dgamma/dbeta are reduced per block
+// in shared memory and added to global with one atomic per column per block.
+// ------------------------------------------------------------------------------------------
+template <int E, bool DY_BF16>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
+              const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, float* __restrict__ dx, int accumulate_dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+  constexpr int V = E / 128;
+  __shared__ float s_dg[E], s_db[E];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) s_dg[i] = s_db[i] = 0.f;
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int l = lane_id();
+  float4 gam[V], adg[V], adb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + l + i * 32);
+    adg[i] = adb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = warp; row < M; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[V], dyv[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c4 = l + i * 32;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)row * E) + c4);
+      if (DY_BF16) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>((const bf16*)dy_ + (long long)row * E) + c4);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        dyv[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        dyv[i] = __ldg(reinterpret_cast<const float4*>((const float*)dy_ + (long long)row * E) + c4);
+      }
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      const float4 g = make_float4(dyv[i].x * gam[i].x, dyv[i].y * gam[i].y, dyv[i].z * gam[i].z,
+                                   dyv[i].w * gam[i].w);
+      s1 += g.x + g.y + g.z + g.w;
+      s2 += g.x * xh[i].x + g.y * xh[i].y + g.z * xh[i].z + g.w * xh[i].w;
+      adg[i].x += dyv[i].x * xh[i].x; adg[i].y += dyv[i].y * xh[i].y;
+      adg[i].z += dyv[i].z * xh[i].z; adg[i].w += dyv[i].w * xh[i].w;
+      adb[i].x += dyv[i].x; adb[i].y += dyv[i].y; adb[i].z += dyv[i].z; adb[i].w += dyv[i].w;
+    }
+    const float m1 = warp_sum(s1) * (1.f / E), m2 = warp_sum(s2) * (1.f / E);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c4 = l + i * 32;
+      float4 o;
+      o.x = rs * (dyv[i].x * gam[i].x - m1 - xh[i].x * m2);
+      o.y = rs * (dyv[i].y * gam[i].y - m1 - xh[i].y * m2);
+      o.z = rs * (dyv[i].z * gam[i].z - m1 - xh[i].z * m2);
+      o.w = rs * (dyv[i].w * gam[i].w - m1 - xh[i].w * m2);
+      float4* dst = reinterpret_cast<float4*>(dx + (long long)row * E) + c4;
+      if (accumulate_dx) {
+        const float4 old = *dst;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *dst = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (l + i * 32) * 4;
+    atomicAdd(&s_dg[c], adg[i].x); atomicAdd(&s_dg[c + 1], adg[i].y);
+    atomicAdd(&s_dg[c + 2], adg[i].z); atomicAdd(&s_dg[c + 3], adg[i].w);
+    atomicAdd(&s_db[c], adb[i].x); atomicAdd(&s_db[c + 1], adb[i].y);
+    atomicAdd(&s_db[c + 2], adb[i].z); atomicAdd(&s_db[c + 3], adb[i].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, s_dg[i]);
+    if (dbeta) atomicAdd(dbeta + i, s_db[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (weights, activations), 8 elements per thread.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      *reinterpret_cast<uint4*>(dst + i) =
+          make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                     *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Column sums of a [M, N] matrix (bf16 or fp32 in), optionally emitting a bf16 copy.
+// grid = (ceil(N/64), row_splits); each warp owns 64 columns (2 per lane) of a row subset.
+// ------------------------------------------------------------------------------------------
+template <bool IN_BF16>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x_, long long ld, bf16* __restrict__ copy16, long long ldc,
+              float* __restrict__ out, int M, int N) {
+  __shared__ float2 part[8][32];
+  const int warp = threadIdx.x >> 5, l = lane_id();
+  const int col = blockIdx.x * 64 + l * 2;
+  const int rows_per = cdiv(M, (int)gridDim.y);
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float2 acc = make_float2(0.f, 0.f);
+  if (col < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      float2 v;
+      if (IN_BF16) {
+        v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>((const bf16*)x_ + (long long)r * ld + col));
+      } else {
+        v = *reinterpret_cast<const float2*>((const float*)x_ + (long long)r * ld + col);
+        if (copy16)
+          *reinterpret_cast<__nv_bfloat162*>(copy16 + (long long)r * ldc + col) = __floats2bfloat162_rn(v.x, v.y);
+      }
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+  }
+  part[warp][l] = acc;
+  __syncthreads();
+  if (warp == 0 && col < N) {
+    float2 s = part[0][l];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      s.x += part[w][l].x;
+      s.y += part[w][l].y;
+    }
+    atomicAdd(out + col, s.x);
+    atomicAdd(out + col + 1, s.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Decoder embedding build (src/model.py:253-277): E[b,p] = table[id(b,p)] (+ ctx[b, j/two_sent]
+// for lyric position j = p - P < S*two_sent), cast to bf16 as the projector GEMM's A operand.
+// ctx rows are ordered (s, b): row = s*B + b. One block per (b, p) row, 8 elements per thread.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(const float* __restrict__ table, const int* __restrict__ topic_ids,
+                 const int* __restrict__ input_ids, const float* __restrict__ ctx,
+                 bf16* __restrict__ out, int B, int P, int T, int S, int two_sent, int D) {
+  const int row = blockIdx.x;
+  const int L = P + T;
+  const int b = row / L, p = row - b * L;
+  int id, k = -1;
+  if (p < P) {
+    id = topic_ids[b * P + p];
+  } else {
+    const int j = p - P;
+    id = input_ids[b * T + j];
+    if (j / two_sent < S) k = j / two_sent;
+  }
+  const float* trow = table + (long long)id * D;
+  const float* crow = k >= 0 ? ctx + ((long long)k * B + b) * D : nullptr;
+  for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(trow + c));
+    float4 d = __ldg(reinterpret_cast<const float4*>(trow + c + 4));
+    if (crow) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(crow + c));
+      const float4 f = __ldg(reinterpret_cast<const float4*>(crow + c + 4));
+      a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+      d.x += f.x; d.y += f.y; d.z += f.z; d.w += f.w;
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(d.x, d.y), p3 = __floats2bfloat162_rn(d.z, d.w);
+    *reinterpret_cast<uint4*>(out + (long long)row * D + c) =
+        make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                   *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+  }
+}
+
+// Backward of the context add: dctx[s*B+b, :] = sum over the two_sent lyric rows of pair s of
+// dE[b, P + j, :]. The token table is frozen (not a parameter), so nothing else flows.
+// grid = (B*S, D/256); one thread per column pair.
+__global__ void __launch_bounds__(128)
+embed_bwd_kernel(const bf16* __restrict__ dE, bf16* __restrict__ dctx16, float* __restrict__ dctx32,
+                 int B, int P, int T, int S, int two_sent, int D) {
+  const int bs = blockIdx.x;
+  const int b = bs / S, s = bs - b * S;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 2;
+  if (c >= D) return;
+  const int L = P + T;
+  const int j0 = s * two_sent, j1 = min(T, j0 + two_sent);
+  float2 acc = make_float2(0.f, 0.f);
+  for (int j = j0; j < j1; ++j) {
+    const float2 v = __bfloat1622float2(
+        *reinterpret_cast<const __nv_bfloat162*>(dE + ((long long)b * L + P + j) * D + c));
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  const long long o = ((long long)s * B + b) * D + c;
+  if (dctx16) *reinterpret_cast<__nv_bfloat162*>(dctx16 + o) = __floats2bfloat162_rn(acc.x, acc.y);
+  if (dctx32) *reinterpret_cast<float2*>(dctx32 + o) = acc;
+}
+
+// Backward of "h0 = proj + wpe[pos] + wte[type]" (HF modeling_gpt2.py:579-612):
+// dwpe[p, :] += sum_b dh[b*L + p, :]  — one thread per (p, column), deterministic.
+__global__ void __launch_bounds__(256)
+posadd_bwd_kernel(const float* __restrict__ dh, float* __restrict__ dwpe, int B, int L, int E) {
+  const int p = blockIdx.x;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= E) return;
+  float a = 0.f;
+  for (int b = 0; b < B; ++b) a += dh[((long long)b * L + p) * E + c];
+  dwpe[(long long)p * E + c] += a;
+}
+// dwte[type_ids[row], :] += dh[row, :]. Only a handful of distinct type ids exist, so each block
+// first reduces its 128 rows per type in shared memory, then issues one atomic per (type, col).
+constexpr int TYPE_SLOTS = 16;
+__global__ void __launch_bounds__(128)
+typeadd_bwd_kernel(const float* __restrict__ dh, const int* __restrict__ type_ids,
+                   float* __restrict__ dwte, int M, int E) {
+  __shared__ float acc[TYPE_SLOTS][128];
+  __shared__ int touched[TYPE_SLOTS];
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  for (int t = 0; t < TYPE_SLOTS; ++t) acc[t][threadIdx.x] = 0.f;
+  if (threadIdx.x < TYPE_SLOTS) touched[threadIdx.x] = 0;
+  __syncthreads();
+  const int r0 = blockIdx.x * 128, r1 = min(M, r0 + 128);
+  for (int r = r0; r < r1; ++r) {
+    const int t = type_ids[r];
+    const float v = c < E ? dh[(long long)r * E + c] : 0.f;
+    if (t < TYPE_SLOTS) {
+      acc[t][threadIdx.x] += v;
+      if (threadIdx.x == 0) touched[t] = 1;
+    } else if (c < E) {
+      atomicAdd(dwte + (long long)t * E + c, v);
+    }
+  }
+  __syncthreads();
+  if (c < E)
+    for (int t = 0; t < TYPE_SLOTS; ++t)
+      if (touched[t]) atomicAdd(dwte + (long long)t * E + c, acc[t][threadIdx.x]);
+}
+// fp32 [M, V] contiguous gradient -> bf16 [M, Vp] padded GEMM operand (generic MyLoss path)
+__global__ void __launch_bounds__(256)
+dlogits_cvt_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int V, int Vp) {
+  const long long row = blockIdx.x;
+  for (int c = threadIdx.x; c < Vp; c += 256)
+    dst[row * Vp + c] = __float2bfloat16(c < V ? __ldg(src + row * V + c) : 0.f);
+}
+
+}  // namespace
+
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y16, float* y32,
+                  float* mean, float* rstd, int M, int E, float eps, cudaStream_t st) {
+  MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
+  const int blocks = min(cdiv(M, 8), num_sms() * 8);
+  if (E == 768) ln_fwd_kernel<768><<<blocks, 256, 0, st>>>(x, gamma, beta, y16, y32, mean, rstd, M, eps);
+  else ln_fwd_kernel<512><<<blocks, 256, 0, st>>>(x, gamma, beta, y16, y32, mean, rstd, M, eps);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd,
+                  const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
+                  int M, int E, cudaStream_t st) {
+  MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
+  const int blocks = min(cdiv(M, 8), num_sms() * 2);
+#define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, M)
+  if (E == 768) { if (dy_bf16) LNB(768, true); else LNB(768, false); }
+  else { if (dy_bf16) LNB(512, true); else LNB(512, false); }
+#undef LNB
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long long want = cdivll(n, 8 * 256);
+  const int blocks = (int)(want < (long long)num_sms() * 16 ? want : (long long)num_sms() * 16);
+  cast_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc, float* out, int M,
+           int N, cudaStream_t st) {
+  MMTG_CHECK_ARG(N % 2 == 0 && ld % 2 == 0, "colsum needs even N and pitch");
+  int splits = cdiv(num_sms() * 4, cdiv(N, 64));
+  splits = max(1, min(splits, cdiv(M, 32)));
+  dim3 grid(cdiv(N, 64), splits);
+  if (x_bf16) colsum_kernel<true><<<grid, 256, 0, st>>>(x, ld, nullptr, 0, out, M, N);
+  else colsum_kernel<false><<<grid, 256, 0, st>>>(x, ld, copy16, ldc, out, M, N);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int embed_fwd(const float* table, const int* topic_ids, const int* input_ids, const float* ctx,
+              bf16* out, int B, int P, int T, int S, int two_sent, int D, cudaStream_t st) {
+  MMTG_CHECK_ARG(D % 8 == 0, "embedding width must be a multiple of 8");
+  embed_fwd_kernel<<<B * (P + T), 256, 0, st>>>(table, topic_ids, input_ids, ctx, out, B, P, T, S, two_sent, D);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int embed_bwd(const bf16* dE, bf16* dctx16, float* dctx32, int B, int P, int T, int S, int two_sent,
+              int D, cudaStream_t st) {
+  dim3 grid(B * S, cdiv(D, 256));
+  embed_bwd_kernel<<<grid, 128, 0, st>>>(dE, dctx16, dctx32, B, P, T, S, two_sent, D);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int posadd_bwd(const float* dh, float* dwpe, int B, int L, int E, cudaStream_t st) {
+  dim3 grid(L, cdiv(E, 256));
+  posadd_bwd_kernel<<<grid, 256, 0, st>>>(dh, dwpe, B, L, E);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+int typeadd_bwd(const float* dh, const int* type_ids, float* dwte, int M, int E, cudaStream_t st) {
+  dim3 grid(cdiv(M, 128), cdiv(E, 128));
+  typeadd_bwd_kernel<<<grid, 128, 0, st>>>(dh, type_ids, dwte, M, E);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+int dlogits_f32_to_bf16(const float* src, bf16* dst, int M, int V, int Vp, cudaStream_t st) {
+  dlogits_cvt_kernel<<<M, 256, 0, st>>>(src, dst, V, Vp);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace mmtg
+
+using namespace mmtg;
+
+extern "C" int mmtg_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                                  float* y_f32, float* mean, float* rstd, int32_t M, int32_t E,
+                                  float eps, void* stream) {
+  MMTG_CHECK_ARG(x && gamma && beta && (y_bf16 || y_f32) && M > 0, "bad layernorm args");
+  return layernorm_fwd(x, gamma, beta, (bf16*)y_bf16, y_f32, mean, rstd, M, E, eps, (cudaStream_t)stream);
+}
+extern "C" int mmtg_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const float* x, const float* mean,
+                                  const float* rstd, const float* gamma, float* dx,
+                                  int32_t accumulate_dx, float* dgamma, float* dbeta, int32_t M,
+                                  int32_t E, void* stream) {
+  MMTG_CHECK_ARG(dy && x && mean && rstd && gamma && dx && M > 0, "bad layernorm bwd args");
+  return layernorm_bwd(dy, dy_is_bf16, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, M, E,
+                       (cudaStream_t)stream);
+}
+extern "C" int mmtg_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  MMTG_CHECK_ARG(src && dst && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "cast needs 16-byte aligned buffers");
+  return cast_bf16(src, (bf16*)dst, n, (cudaStream_t)stream);
+}
+extern "C" int mmtg_colsum(const void* x, int32_t x_is_bf16, int64_t ld, void* copy_bf16, int64_t ldc,
+                           float* out, int32_t M, int32_t N, void* stream) {
+  MMTG_CHECK_ARG(x && out && M > 0 && N > 0, "bad colsum args");
+  return colsum(x, x_is_bf16, ld, (bf16*)copy_bf16, ldc, out, M, N, (cudaStream_t)stream);
+}
+extern "C" int mmtg_embed_fwd(const float* table, const int32_t* topic_ids, const int32_t* input_ids,
+                              const float* ctx, void* out_bf16, int32_t B, int32_t P, int32_t T,
+                              int32_t S, int32_t two_sent, int32_t D, void* stream) {
+  MMTG_CHECK_ARG(table && topic_ids && input_ids && out_bf16, "bad embed args");
+  return embed_fwd(table, topic_ids, input_ids, ctx, (bf16*)out_bf16, B, P, T, S, two_sent, D, (cudaStream_t)stream);
+}
+extern "C" int mmtg_embed_bwd(const void* dE_bf16, void* dctx_bf16, float* dctx_f32, int32_t B, int32_t P,
+                              int32_t T, int32_t S, int32_t two_sent, int32_t D, void* stream) {
+  MMTG_CHECK_ARG(dE_bf16 && (dctx_bf16 || dctx_f32), "bad embed bwd args");
+  return embed_bwd((const bf16*)dE_bf16, (bf16*)dctx_bf16, dctx_f32, B, P, T, S, two_sent, D, (cudaStream_t)stream);
+}

@@ -1,0 +1,460 @@
+// Native orchestration of the MMTG training hot path on ONE stream:
+//   forward  = MMTG.forward, training branch (src/model.py:356-400): encoder -> LayerNorms ->
+//              alpha attention x2 (+KL) -> beta gate -> embedding build -> projector -> 12 GPT-2
+//              blocks -> ln_f -> tied lm_head (+ fused row log-sum-exp) -> HF causal-LM loss;
+//   backward = the hand-derived reverse of all of the above, split in stages so the host can
+//              overlap a bucketed gradient all-reduce with the remaining backward work.
+// No tensor library, no allocation: the caller provides one workspace, carved here.
+//
+// Operand layouts (why no transposes exist anywhere):
+//   HF Conv1D weight W[in,out]:  forward  y = x W      -> B operand MN-major (native storage)
+//                                dgrad   dx = dy W^T   -> B operand K-major  (native storage)
+//                                wgrad   dW = x^T dy   -> A, B operands MN-major
+//   nn.Linear weight W[out,in]:  forward K-major, dgrad MN-major, wgrad dW = dy^T x (MN, MN)
+#include <string.h>
+
+#include "../../include/mmtg_b200.h"
+#include "ops.h"
+
+namespace mmtg {
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct LayerWs {
+  float* h_in;  // alias of the previous layer's output (residual stream), fp32 [M,E]
+  bf16* x1;
+  float *mean1, *rstd1;
+  bf16* qkv;
+  bf16* att;
+  float* lse;
+  float* h_mid;
+  bf16* x2;
+  float *mean2, *rstd2;
+  bf16 *u, *a;
+  float* h_out;
+};
+
+struct Ws {
+  // decoder forward
+  bf16* emb16;
+  bf16* p1;
+  float* h0;
+  LayerWs layer[MMTG_MAX_LAYERS];
+  bf16* xf;
+  float *meanf, *rstdf;
+  float* lse_part;
+  float* lse;
+  float* hf_sum;
+  // decoder backward
+  bf16* dlogits16;
+  float* dh;
+  bf16 *g16, *du, *dx, *datt, *dqkv, *dp1, *dE;
+  float* delta;
+  // encoder forward
+  bf16 *x_topic16, *x_mod16[2];
+  float* topic_pre;
+  float* gi_all[2];
+  float* gh;
+  float* gru_save[2];
+  float* hout[2];
+  bf16* hout16[2];
+  float *topic_ln, *topic_mean, *topic_rstd;
+  bf16* ln16[2];
+  float *ln_mean[2], *ln_rstd[2];
+  float* aqkv[2];
+  float* actx[2];
+  float* aprobs[2];
+  float* klpart;
+  bf16* o16;
+  float* att3;
+  float* ctx_out;
+  // encoder backward
+  bf16 *dctx16, *do16;
+  float *dtopic_ln, *dactx[2];
+  bf16* daqkv16;
+  float* dln;
+  float* dhout;
+  bf16 *dgi16, *dgh16;
+  float *dhz, *dcarry;
+  float* dtopic_pre;
+  bf16* dtopic_pre16;
+  size_t bytes;
+};
+
+// Carve the workspace. Called with base == nullptr to size it.
+void carve(const mmtg_dims& d, uint8_t* base, Ws* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t M = (size_t)d.B * d.L, E = d.E, SB = (size_t)d.S * d.B, He = d.He, Dw = d.Dw;
+  auto f32 = [&](size_t n) { return (float*)take(n * 4); };
+  auto b16 = [&](size_t n) { return (bf16*)take(n * 2); };
+  w->emb16 = b16(M * Dw);
+  w->p1 = b16(M * He);
+  w->h0 = f32(M * E);
+  float* prev = w->h0;
+  for (int l = 0; l < d.NL; ++l) {
+    LayerWs& L = w->layer[l];
+    L.h_in = prev;
+    L.x1 = b16(M * E);
+    L.mean1 = f32(M);
+    L.rstd1 = f32(M);
+    L.qkv = b16(M * 3 * E);
+    L.att = b16(M * E);
+    L.lse = f32((size_t)d.B * d.NH * d.L);
+    L.h_mid = f32(M * E);
+    L.x2 = b16(M * E);
+    L.mean2 = f32(M);
+    L.rstd2 = f32(M);
+    L.u = b16(M * 4 * E);
+    L.a = b16(M * 4 * E);
+    L.h_out = f32(M * E);
+    prev = L.h_out;
+  }
+  w->xf = b16(M * E);
+  w->meanf = f32(M);
+  w->rstdf = f32(M);
+  const size_t nt = (size_t)cdiv(d.V, 128);  // enough for either tile width
+  w->lse_part = f32(nt * M * 2);
+  w->lse = f32(M);
+  w->hf_sum = f32(d.B);
+  w->dlogits16 = b16(M * d.Vp);
+  w->dh = f32(M * E);
+  w->g16 = b16(M * E);
+  w->du = b16(M * 4 * E);
+  w->dx = b16(M * E);
+  w->datt = b16(M * E);
+  w->dqkv = b16(M * 3 * E);
+  w->dp1 = b16(M * He);
+  w->dE = b16(M * Dw);
+  w->delta = f32((size_t)d.B * d.NH * d.L);
+  // encoder
+  w->x_topic16 = b16((size_t)d.B * Dw);
+  for (int m = 0; m < 2; ++m) w->x_mod16[m] = b16(SB * Dw);
+  w->topic_pre = f32((size_t)d.B * He);
+  for (int m = 0; m < 2; ++m) w->gi_all[m] = f32(SB * 3 * He);
+  w->gh = f32((size_t)d.B * 3 * He);
+  for (int m = 0; m < 2; ++m) w->gru_save[m] = f32(SB * 4 * He);
+  for (int m = 0; m < 2; ++m) w->hout[m] = f32(SB * He);
+  for (int m = 0; m < 2; ++m) w->hout16[m] = b16(SB * He);
+  w->topic_ln = f32((size_t)d.B * He);
+  w->topic_mean = f32(d.B);
+  w->topic_rstd = f32(d.B);
+  for (int m = 0; m < 2; ++m) {
+    w->ln16[m] = b16(SB * He);
+    w->ln_mean[m] = f32(SB);
+    w->ln_rstd[m] = f32(SB);
+    w->aqkv[m] = f32(SB * 3 * He);
+    w->actx[m] = f32(SB * He);
+    w->aprobs[m] = f32((size_t)d.B * d.alpha_heads * d.S * d.S);
+  }
+  w->klpart = f32((size_t)2 * d.B * d.alpha_heads);
+  w->o16 = b16(SB * He);
+  w->att3 = f32(SB * 3);
+  w->ctx_out = f32(SB * Dw);
+  w->dctx16 = b16(SB * Dw);
+  w->do16 = b16(SB * He);
+  w->dtopic_ln = f32((size_t)d.B * He);
+  for (int m = 0; m < 2; ++m) w->dactx[m] = f32(SB * He);
+  w->daqkv16 = b16(SB * 3 * He);
+  w->dln = f32(SB * He);
+  w->dhout = f32(SB * He);
+  w->dgi16 = b16(SB * 3 * He);
+  w->dgh16 = b16(SB * 3 * He);
+  w->dhz = f32((size_t)d.B * He);
+  w->dcarry = f32((size_t)d.B * He);
+  w->dtopic_pre = f32((size_t)d.B * He);
+  w->dtopic_pre16 = b16((size_t)d.B * He);
+  w->bytes = off;
+}
+
+int check_dims(const mmtg_dims& d) {
+  MMTG_CHECK_ARG(d.B > 0 && d.L == d.P + d.T && d.T > 1, "bad dims B=%d P=%d T=%d L=%d", d.B, d.P, d.T, d.L);
+  MMTG_CHECK_ARG(d.NL > 0 && d.NL <= MMTG_MAX_LAYERS, "n_layer %d out of range", d.NL);
+  MMTG_CHECK_ARG(d.E == d.NH * 64, "head_dim must be 64 (E=%d NH=%d)", d.E, d.NH);
+  MMTG_CHECK_ARG(d.Vp >= d.V && d.Vp % 8 == 0, "Vp must be V rounded up to a multiple of 8");
+  MMTG_CHECK_ARG(d.L <= d.n_pos, "sequence %d exceeds n_positions %d", d.L, d.n_pos);
+  MMTG_CHECK_ARG(d.He % d.alpha_heads == 0, "bad alpha heads");
+  return 0;
+}
+
+// Small builder around mmtg_gemm_args.
+struct Gemm {
+  mmtg_gemm_args a;
+  Gemm(const void* A, long long lda, bool a_mn, const void* B, long long ldb, bool b_mn, int M, int N,
+       int K) {
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.lda = lda; a.a_mn_major = a_mn;
+    a.B = B; a.ldb = ldb; a.b_mn_major = b_mn;
+    a.M = M; a.N = N; a.K = K;
+  }
+  Gemm& out_f32(float* o, long long ld) { a.out = o; a.ldo = ld; a.out_dtype = MMTG_F32; return *this; }
+  Gemm& out_bf16(bf16* o, long long ld) { a.out = o; a.ldo = ld; a.out_dtype = MMTG_BF16; return *this; }
+  Gemm& bias(const float* b) { a.bias = b; return *this; }
+  Gemm& act(int x) { a.act = x; return *this; }
+  Gemm& out2(bf16* o, long long ld) { a.out2 = o; a.ldo2 = ld; return *this; }
+  Gemm& residual(const float* r, long long ld) { a.residual = r; a.ldr = ld; return *this; }
+  Gemm& dgelu(const bf16* u, long long ld) { a.dgelu_src = u; a.ldg = ld; return *this; }
+  Gemm& dtanh(const bf16* y, long long ld) { a.dgelu_src = y; a.ldg = ld; a.dact_tanh_out = 1; return *this; }
+  Gemm& colsum(float* c) { a.colsum = c; return *this; }
+  Gemm& accumulate(int split = 1) { a.accumulate = 1; a.split_k = split; return *this; }
+  Gemm& lse(float* p, int bn) { a.lse_partial = p; a.block_n = bn; return *this; }
+  int run(cudaStream_t st) { return mmtg_gemm_bf16(&a, (void*)st); }
+};
+
+// wgrad: dW[rows, cols] += X^T Y with X [K, rows] and Y [K, cols] row-major activations.
+// Split-K picks enough work units to cover the machine (output tiles are few).
+int wgrad(const bf16* X, long long ldx, const bf16* Y, long long ldy, float* dW, long long ldw,
+          int rows, int cols, int K, cudaStream_t st) {
+  const int tiles = cdiv(rows, 128) * cdiv(cols, 128);
+  int split = 1;
+  if (tiles < num_sms()) {
+    split = cdiv(num_sms(), tiles);
+    const int max_split = (K + 511) / 512;  // keep >= 8 k-blocks per split
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+  }
+  Gemm g(X, ldx, true, Y, ldy, true, rows, cols, K);
+  g.out_f32(dW, ldw).accumulate(split);
+  g.a.block_n = 128;
+  return g.run(st);
+}
+
+}  // namespace
+
+}  // namespace mmtg
+
+using namespace mmtg;
+
+extern "C" int64_t mmtg_train_workspace_bytes(const mmtg_dims* dims) {
+  if (!dims || check_dims(*dims) != 0) return -1;
+  Ws w;
+  carve(*dims, nullptr, &w);
+  return (int64_t)w.bytes;
+}
+extern "C" float* mmtg_ws_lse(const mmtg_dims* dims, void* workspace) {
+  Ws w;
+  carve(*dims, (uint8_t*)workspace, &w);
+  return w.lse;
+}
+extern "C" void* mmtg_ws_dlogits_bf16(const mmtg_dims* dims, void* workspace) {
+  Ws w;
+  carve(*dims, (uint8_t*)workspace, &w);
+  return w.dlogits16;
+}
+extern "C" int mmtg_dlogits_from_f32(const mmtg_dims* dims, void* workspace, const float* src, void* stream) {
+  MMTG_CHECK_ARG(dims && workspace && src, "null argument");
+  Ws w;
+  carve(*dims, (uint8_t*)workspace, &w);
+  return dlogits_f32_to_bf16(src, w.dlogits16, dims->B * dims->L, dims->V, dims->Vp, (cudaStream_t)stream);
+}
+
+extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
+                                  int64_t workspace_bytes, float* logits, float* scalars_out,
+                                  int32_t save_for_backward, void* stream) {
+  (void)save_for_backward;
+  MMTG_CHECK_ARG(m && b && workspace && logits && scalars_out, "null argument");
+  const mmtg_dims& d = m->dims;
+  MMTG_TRY(check_dims(d));
+  Ws w;
+  carve(d, (uint8_t*)workspace, &w);
+  MMTG_CHECK_ARG((int64_t)w.bytes <= workspace_bytes, "workspace too small: need %zu, have %lld", w.bytes,
+                 (long long)workspace_bytes);
+  MMTG_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* P = m->params;
+  const bf16* W = (const bf16*)m->params_bf16;
+  const mmtg_param_offsets& o = m->off;
+  const int B = d.B, S = d.S, He = d.He, Dw = d.Dw, E = d.E, SB = d.S * d.B, M = d.B * d.L;
+  const float eps = 1e-5f;
+
+  // ---------------- encoder (src/model.py:63-81) ----------------
+  MMTG_TRY(pack_sb(b->topic_emb, w.x_topic16, B, 1, Dw, st));
+  MMTG_TRY(pack_sb(b->img_embs, w.x_mod16[0], B, S, Dw, st));
+  MMTG_TRY(pack_sb(b->txt_embs, w.x_mod16[1], B, S, Dw, st));
+  MMTG_TRY(Gemm(w.x_topic16, Dw, false, W + o.topic_w, Dw, false, B, He, Dw)
+               .out_f32(w.topic_pre, He).bias(P + o.topic_b).run(st));
+  for (int md = 0; md < 2; ++md) {
+    MMTG_TRY(Gemm(w.x_mod16[md], Dw, false, W + o.gru_w_ih[md], Dw, false, SB, 3 * He, Dw)
+                 .out_f32(w.gi_all[md], 3 * He).bias(P + o.gru_b_ih[md]).run(st));
+    for (int t = 0; t < S; ++t) {
+      const float* hp = t > 0 ? w.hout[md] + (size_t)(t - 1) * B * He : nullptr;
+      if (t > 0)
+        MMTG_TRY(Gemm(w.hout16[md] + (size_t)(t - 1) * B * He, He, false, W + o.gru_w_hh[md], He, false, B,
+                      3 * He, He)
+                     .out_f32(w.gh, 3 * He).bias(P + o.gru_b_hh[md]).run(st));
+      MMTG_TRY(gru_gate_fwd(w.gi_all[md] + (size_t)t * B * 3 * He, t > 0 ? w.gh : nullptr,
+                            P + o.gru_b_hh[md], hp, w.hout[md] + (size_t)t * B * He,
+                            w.hout16[md] + (size_t)t * B * He, w.gru_save[md] + (size_t)t * B * 4 * He, B,
+                            He, st));
+    }
+  }
+  // ---------------- LayerNorms (src/model.py:380-382) ----------------
+  MMTG_TRY(layernorm_fwd(w.topic_pre, P + o.enc_ln_w[0], P + o.enc_ln_b[0], nullptr, w.topic_ln,
+                         w.topic_mean, w.topic_rstd, B, He, eps, st));
+  for (int md = 0; md < 2; ++md)
+    MMTG_TRY(layernorm_fwd(w.hout[md], P + o.enc_ln_w[1 + md], P + o.enc_ln_b[1 + md], w.ln16[md],
+                           nullptr, w.ln_mean[md], w.ln_rstd[md], SB, He, eps, st));
+  // ---------------- alpha attention + KL (src/model.py:133-161) ----------------
+  for (int md = 0; md < 2; ++md) {
+    MMTG_TRY(Gemm(w.ln16[md], He, false, W + o.alpha_qkv_w[md], He, false, SB, 3 * He, He)
+                 .out_f32(w.aqkv[md], 3 * He).bias(P + o.alpha_qkv_b[md]).run(st));
+    MMTG_TRY(alpha_fwd(w.aqkv[md], w.actx[md], w.aprobs[md], w.klpart + (size_t)md * B * d.alpha_heads,
+                       B, d.alpha_heads, S, He / d.alpha_heads, st));
+  }
+  MMTG_TRY(sum_scale(w.klpart, scalars_out + 1, 2 * B * d.alpha_heads, 1.f / (float)(S * B), st));
+  // ---------------- beta gate + out_linear (src/model.py:181-202) ----------------
+  MMTG_TRY(beta_fwd(w.topic_ln, w.actx[0], w.actx[1], P + o.beta_att_w, P + o.beta_att_b, w.o16,
+                    w.att3, B, S, He, st));
+  MMTG_TRY(Gemm(w.o16, He, false, W + o.beta_out_w, He, false, SB, Dw, He)
+               .out_f32(w.ctx_out, Dw).bias(P + o.beta_out_b).run(st));
+  // ---------------- decoder embedding + projector (src/model.py:253-281) ----------------
+  MMTG_TRY(embed_fwd(m->token_table, b->topic_ids, b->targets, w.ctx_out, w.emb16, B, d.P, d.T, S,
+                     d.two_sent, Dw, st));
+  MMTG_TRY(Gemm(w.emb16, Dw, false, W + o.proj1_w, Dw, false, M, He, Dw)
+               .out_bf16(w.p1, He).bias(P + o.proj1_b).act(MMTG_ACT_TANH).run(st));
+  {  // h0 = p1 W2^T + b2 + wpe[pos] + wte[type]   (HF modeling_gpt2.py:579-612)
+    Gemm g(w.p1, He, false, W + o.proj2_w, He, false, M, E, He);
+    g.out_f32(w.h0, E).bias(P + o.proj2_b);
+    g.a.rowtab0 = P + o.wpe; g.a.ldt0 = E; g.a.rowmod0 = d.L;
+    g.a.rowtab1 = P + o.wte; g.a.ldt1 = E; g.a.rowidx1 = b->type_ids;
+    MMTG_TRY(g.run(st));
+  }
+  // ---------------- GPT-2 blocks (HF modeling_gpt2.py:262-309) ----------------
+  for (int l = 0; l < d.NL; ++l) {
+    const LayerWs& L = w.layer[l];
+    const mmtg_layer_offsets& lo = o.layer[l];
+    MMTG_TRY(layernorm_fwd(L.h_in, P + lo.ln1_w, P + lo.ln1_b, L.x1, nullptr, L.mean1, L.rstd1, M, E, eps, st));
+    MMTG_TRY(Gemm(L.x1, E, false, W + lo.attn_w, 3 * E, true, M, 3 * E, E)
+                 .out_bf16(L.qkv, 3 * E).bias(P + lo.attn_b).run(st));
+    MMTG_TRY(attn_fwd(L.qkv, b->attn_mask, L.att, L.lse, B, d.L, d.NH, st));
+    MMTG_TRY(Gemm(L.att, E, false, W + lo.proj_w, E, true, M, E, E)
+                 .out_f32(L.h_mid, E).bias(P + lo.proj_b).residual(L.h_in, E).run(st));
+    MMTG_TRY(layernorm_fwd(L.h_mid, P + lo.ln2_w, P + lo.ln2_b, L.x2, nullptr, L.mean2, L.rstd2, M, E, eps, st));
+    MMTG_TRY(Gemm(L.x2, E, false, W + lo.fc_w, 4 * E, true, M, 4 * E, E)
+                 .out_bf16(L.a, 4 * E).out2(L.u, 4 * E).bias(P + lo.fc_b).act(MMTG_ACT_GELU_NEW).run(st));
+    MMTG_TRY(Gemm(L.a, 4 * E, false, W + lo.proj2_w, E, true, M, E, 4 * E)
+                 .out_f32(L.h_out, E).bias(P + lo.proj2_b).residual(L.h_mid, E).run(st));
+  }
+  // ---------------- ln_f + tied lm_head + HF loss ----------------
+  const float* h_last = w.layer[d.NL - 1].h_out;
+  MMTG_TRY(layernorm_fwd(h_last, P + o.lnf_w, P + o.lnf_b, w.xf, nullptr, w.meanf, w.rstdf, M, E, eps, st));
+  const int bn = 256;
+  MMTG_TRY(Gemm(w.xf, E, false, W + o.wte, E, false, M, d.V, E).out_f32(logits, d.V).lse(w.lse_part, bn).run(st));
+  MMTG_TRY(lse_combine(w.lse_part, w.lse, M, cdiv(d.V, bn), st));
+  MMTG_TRY(ce_reduce(logits, d.V, w.lse, b->topic_ids, b->targets, w.hf_sum, nullptr, scalars_out, B,
+                     d.L, d.P, d.T, st));
+  return 0;
+}
+
+extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
+                                   int64_t workspace_bytes, const float* g_kl, int32_t stage_begin,
+                                   int32_t stage_end, void* stream) {
+  MMTG_CHECK_ARG(m && b && workspace && m->grads, "null argument");
+  const mmtg_dims& d = m->dims;
+  MMTG_TRY(check_dims(d));
+  Ws w;
+  carve(d, (uint8_t*)workspace, &w);
+  MMTG_CHECK_ARG((int64_t)w.bytes <= workspace_bytes, "workspace too small");
+  MMTG_CHECK_ARG(stage_begin >= 0 && stage_end <= d.NL + 2 && stage_begin <= stage_end, "bad stage range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* P = m->params;
+  const bf16* W = (const bf16*)m->params_bf16;
+  float* G = m->grads;
+  const mmtg_param_offsets& o = m->off;
+  const int B = d.B, S = d.S, He = d.He, Dw = d.Dw, E = d.E, SB = d.S * d.B, M = d.B * d.L;
+
+  for (int stage = stage_begin; stage < stage_end; ++stage) {
+    if (stage == 0) {
+      // ---------------- lm_head (tied wte) + ln_f ----------------
+      // dxf = dlogits · wte  (B operand: wte [V,E] as MN-major [N=E, K=V])
+      MMTG_TRY(Gemm(w.dlogits16, d.Vp, false, W + o.wte, E, true, M, E, d.V).out_bf16(w.dx, E).run(st));
+      // dwte += dlogits^T · xf
+      MMTG_TRY(wgrad(w.dlogits16, d.Vp, w.xf, E, G + o.wte, E, d.V, E, M, st));
+      MMTG_TRY(layernorm_bwd(w.dx, 1, w.layer[d.NL - 1].h_out, w.meanf, w.rstdf, P + o.lnf_w, w.dh, 0,
+                             G + o.lnf_w, G + o.lnf_b, M, E, st));
+    } else if (stage <= d.NL) {
+      const int l = d.NL - stage;
+      const LayerWs& L = w.layer[l];
+      const mmtg_layer_offsets& lo = o.layer[l];
+      // ---- MLP ----
+      MMTG_TRY(colsum(w.dh, 0, E, w.g16, E, G + lo.proj2_b, M, E, st));
+      MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj2_w, E, false, M, 4 * E, E)
+                   .out_bf16(w.du, 4 * E).dgelu(L.u, 4 * E).colsum(G + lo.fc_b).run(st));
+      MMTG_TRY(wgrad(L.a, 4 * E, w.g16, E, G + lo.proj2_w, E, 4 * E, E, M, st));
+      MMTG_TRY(Gemm(w.du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(w.dx, E).run(st));
+      MMTG_TRY(wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, st));
+      MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_mid, L.mean2, L.rstd2, P + lo.ln2_w, w.dh, 1, G + lo.ln2_w,
+                             G + lo.ln2_b, M, E, st));
+      // ---- attention ----
+      MMTG_TRY(colsum(w.dh, 0, E, w.g16, E, G + lo.proj_b, M, E, st));
+      MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(w.datt, E).run(st));
+      MMTG_TRY(wgrad(L.att, E, w.g16, E, G + lo.proj_w, E, E, E, M, st));
+      MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, w.datt, L.lse, w.delta, w.dqkv, B, d.L, d.NH, st));
+      MMTG_TRY(colsum(w.dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, st));
+      MMTG_TRY(Gemm(w.dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(w.dx, E).run(st));
+      MMTG_TRY(wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, st));
+      MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_in, L.mean1, L.rstd1, P + lo.ln1_w, w.dh, 1, G + lo.ln1_w,
+                             G + lo.ln1_b, M, E, st));
+    } else {
+      // ---------------- embeddings + projector ----------------
+      MMTG_TRY(posadd_bwd(w.dh, G + o.wpe, B, d.L, E, st));
+      MMTG_TRY(typeadd_bwd(w.dh, b->type_ids, G + o.wte, M, E, st));
+      MMTG_TRY(colsum(w.dh, 0, E, w.g16, E, G + o.proj2_b, M, E, st));
+      // dp1 = (g · W2) ⊙ (1 - p1²); W2 [E,He] as MN-major [N=He, K=E]
+      MMTG_TRY(Gemm(w.g16, E, false, W + o.proj2_w, He, true, M, He, E)
+                   .out_bf16(w.dp1, He).dtanh(w.p1, He).colsum(G + o.proj1_b).run(st));
+      MMTG_TRY(wgrad(w.g16, E, w.p1, He, G + o.proj2_w, He, E, He, M, st));
+      MMTG_TRY(Gemm(w.dp1, He, false, W + o.proj1_w, Dw, true, M, Dw, He).out_bf16(w.dE, Dw).run(st));
+      MMTG_TRY(wgrad(w.dp1, He, w.emb16, Dw, G + o.proj1_w, Dw, He, Dw, M, st));
+      MMTG_TRY(embed_bwd(w.dE, w.dctx16, nullptr, B, d.P, d.T, S, d.two_sent, Dw, st));
+      // ---------------- beta gate ----------------
+      MMTG_TRY(colsum(w.dctx16, 1, Dw, nullptr, 0, G + o.beta_out_b, SB, Dw, st));
+      MMTG_TRY(Gemm(w.dctx16, Dw, false, W + o.beta_out_w, He, true, SB, He, Dw).out_bf16(w.do16, He).run(st));
+      MMTG_TRY(wgrad(w.dctx16, Dw, w.o16, He, G + o.beta_out_w, He, Dw, He, SB, st));
+      MMTG_TRY(beta_bwd(w.topic_ln, w.actx[0], w.actx[1], P + o.beta_att_w, w.att3, w.do16, w.dtopic_ln,
+                        w.dactx[0], w.dactx[1], G + o.beta_att_w, G + o.beta_att_b, B, S, He, st));
+      // ---------------- topic branch ----------------
+      MMTG_TRY(layernorm_bwd(w.dtopic_ln, 0, w.topic_pre, w.topic_mean, w.topic_rstd, P + o.enc_ln_w[0],
+                             w.dtopic_pre, 0, G + o.enc_ln_w[0], G + o.enc_ln_b[0], B, He, st));
+      MMTG_TRY(colsum(w.dtopic_pre, 0, He, w.dtopic_pre16, He, G + o.topic_b, B, He, st));
+      MMTG_TRY(wgrad(w.dtopic_pre16, He, w.x_topic16, Dw, G + o.topic_w, Dw, He, Dw, B, st));
+      // ---------------- image / text branches: alpha attention, LayerNorm, GRU ----------------
+      for (int md = 0; md < 2; ++md) {
+        MMTG_TRY(alpha_bwd(w.aqkv[md], w.aprobs[md], w.dactx[md], g_kl, 1.f / (float)(S * B), w.daqkv16, B,
+                           d.alpha_heads, S, He / d.alpha_heads, st));
+        MMTG_TRY(colsum(w.daqkv16, 1, 3 * He, nullptr, 0, G + o.alpha_qkv_b[md], SB, 3 * He, st));
+        // dln = dqkv · Wqkv  (Wqkv [3He, He] as MN-major [N=He, K=3He])
+        MMTG_TRY(Gemm(w.daqkv16, 3 * He, false, W + o.alpha_qkv_w[md], He, true, SB, He, 3 * He)
+                     .out_f32(w.dln, He).run(st));
+        MMTG_TRY(wgrad(w.daqkv16, 3 * He, w.ln16[md], He, G + o.alpha_qkv_w[md], He, 3 * He, He, SB, st));
+        MMTG_TRY(layernorm_bwd(w.dln, 0, w.hout[md], w.ln_mean[md], w.ln_rstd[md], P + o.enc_ln_w[1 + md],
+                               w.dhout, 0, G + o.enc_ln_w[1 + md], G + o.enc_ln_b[1 + md], SB, He, st));
+        // GRU backward through time
+        for (int t = S - 1; t >= 0; --t) {
+          const float* hp = t > 0 ? w.hout[md] + (size_t)(t - 1) * B * He : nullptr;
+          MMTG_TRY(gru_gate_bwd(w.dhout + (size_t)t * B * He, t < S - 1 ? w.dcarry : nullptr,
+                                w.gru_save[md] + (size_t)t * B * 4 * He, hp,
+                                w.dgi16 + (size_t)t * B * 3 * He, w.dgh16 + (size_t)t * B * 3 * He, w.dhz, B,
+                                He, st));
+          if (t > 0)  // carry = dh*z + dgh · W_hh   (W_hh [3He, He] as MN-major [N=He, K=3He])
+            MMTG_TRY(Gemm(w.dgh16 + (size_t)t * B * 3 * He, 3 * He, false, W + o.gru_w_hh[md], He, true, B, He,
+                          3 * He)
+                         .out_f32(w.dcarry, He).residual(w.dhz, He).run(st));
+        }
+        MMTG_TRY(colsum(w.dgi16, 1, 3 * He, nullptr, 0, G + o.gru_b_ih[md], SB, 3 * He, st));
+        MMTG_TRY(colsum(w.dgh16, 1, 3 * He, nullptr, 0, G + o.gru_b_hh[md], SB, 3 * He, st));
+        MMTG_TRY(wgrad(w.dgi16, 3 * He, w.x_mod16[md], Dw, G + o.gru_w_ih[md], Dw, 3 * He, Dw, SB, st));
+        if (S > 1)
+          MMTG_TRY(wgrad(w.dgh16 + (size_t)B * 3 * He, 3 * He, w.hout16[md], He, G + o.gru_w_hh[md], He,
+                         3 * He, He, (S - 1) * B, st));
+      }
+    }
+  }
+  return 0;
+}

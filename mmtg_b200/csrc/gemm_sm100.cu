@@ -49,6 +49,7 @@ struct GemmParams {
   float* colsum;
   float* lse_partial;
   int vec4;
+  int dact_tanh_out;
 };
 
 template <int BN>
@@ -287,8 +288,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int it = 0; it < 8; ++it) {
               const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u[it].x));
               const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u[it].y));
-              v[it][0] *= dgelu_new_f(a.x); v[it][1] *= dgelu_new_f(a.y);
-              v[it][2] *= dgelu_new_f(b.x); v[it][3] *= dgelu_new_f(b.y);
+              if (p.dact_tanh_out) {
+                v[it][0] *= 1.f - a.x * a.x; v[it][1] *= 1.f - a.y * a.y;
+                v[it][2] *= 1.f - b.x * b.x; v[it][3] *= 1.f - b.y * b.y;
+              } else {
+                v[it][0] *= dgelu_new_f(a.x); v[it][1] *= dgelu_new_f(a.y);
+                v[it][2] *= dgelu_new_f(b.x); v[it][3] *= dgelu_new_f(b.y);
+              }
             }
           }
           if (p.residual) {
@@ -555,6 +561,7 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   p.rowtab1 = a->rowtab1; p.rowidx1 = a->rowidx1; p.ldt1 = a->ldt1;
   p.colsum = a->colsum;
   p.lse_partial = a->lse_partial;
+  p.dact_tanh_out = a->dact_tanh_out;
   MMTG_CHECK_ARG(!(p.lse_partial && p.splits > 1), "lse_partial is incompatible with split_k");
   {
     // vector epilogue needs 16-B aligned fp32 rows / 8-B aligned bf16 rows for every operand

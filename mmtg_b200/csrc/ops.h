@@ -1,0 +1,54 @@
+// Internal prototypes of the per-op launchers (defined across the .cu files of this library).
+#pragma once
+#include "common.cuh"
+
+namespace mmtg {
+
+// elementwise.cu
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y16, float* y32,
+                  float* mean, float* rstd, int M, int E, float eps, cudaStream_t st);
+int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd,
+                  const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
+                  int M, int E, cudaStream_t st);
+int cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
+int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc, float* out, int M,
+           int N, cudaStream_t st);
+int embed_fwd(const float* table, const int* topic_ids, const int* input_ids, const float* ctx,
+              bf16* out, int B, int P, int T, int S, int two_sent, int D, cudaStream_t st);
+int embed_bwd(const bf16* dE, bf16* dctx16, float* dctx32, int B, int P, int T, int S, int two_sent,
+              int D, cudaStream_t st);
+int posadd_bwd(const float* dh, float* dwpe, int B, int L, int E, cudaStream_t st);
+int typeadd_bwd(const float* dh, const int* type_ids, float* dwte, int M, int E, cudaStream_t st);
+int dlogits_f32_to_bf16(const float* src, bf16* dst, int M, int V, int Vp, cudaStream_t st);
+
+// attention.cu
+int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
+             cudaStream_t st);
+int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
+             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st);
+
+// loss.cu
+int lse_rows(const float* logits, long long ld, float* lse, int M, int V, cudaStream_t st);
+int lse_combine(const float* part, float* lse, int M, int ntiles, cudaStream_t st);
+int ce_reduce(const float* logits, long long ld, const float* lse, const int* topic_ids,
+              const int* targets, float* hf_sum, float* ce, float* hf_loss, int B, int L, int P, int T,
+              cudaStream_t st);
+int sum_scale(const float* x, float* out, int n, float scale, cudaStream_t st);
+
+// encoder.cu
+int pack_sb(const float* in, bf16* out, int B, int S, int D, cudaStream_t st);
+int gru_gate_fwd(const float* gi, const float* gh, const float* b_hh, const float* h_prev,
+                 float* h_out, bf16* h_out16, float* save, int B, int H, cudaStream_t st);
+int gru_gate_bwd(const float* dh_out, const float* dh_carry, const float* save, const float* h_prev,
+                 bf16* dgi, bf16* dgh, float* dhz, int B, int H, cudaStream_t st);
+int alpha_fwd(const float* qkv, float* ctx, float* probs, float* klpart, int B, int heads, int S,
+              int DH, cudaStream_t st);
+int alpha_bwd(const float* qkv, const float* probs, const float* dctx, const float* g_kl,
+              float kl_scale, bf16* dqkv, int B, int heads, int S, int DH, cudaStream_t st);
+int beta_fwd(const float* topic, const float* img, const float* txt, const float* att_w,
+             const float* att_b, bf16* o16, float* att, int B, int S, int H, cudaStream_t st);
+int beta_bwd(const float* topic, const float* img, const float* txt, const float* att_w,
+             const float* att, const bf16* do16, float* dtopic, float* dimg, float* dtxt,
+             float* datt_w, float* datt_b, int B, int S, int H, cudaStream_t st);
+
+}  // namespace mmtg

@@ -62,3 +62,51 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         a.lse_partial = lse_partial.data_ptr()
     _lib.check(_lib.lib().mmtg_gemm_bf16(C.byref(a), C.c_void_p(_lib.stream_ptr())), "mmtg_gemm_bf16")
     return out
+
+
+def _st():
+    return C.c_void_p(_lib.stream_ptr())
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, want_bf16=True, want_f32=False):
+    M, E = x.shape
+    y16 = torch.empty(M, E, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    y32 = torch.empty(M, E, device=x.device) if want_f32 else None
+    mean, rstd = torch.empty(M, device=x.device), torch.empty(M, device=x.device)
+    _lib.check(_lib.lib().mmtg_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y16), _p(y32), _p(mean), _p(rstd),
+                                             M, E, C.c_float(eps), _st()), "mmtg_layernorm_fwd")
+    return y16, y32, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta):
+    M, E = x.shape
+    _lib.check(_lib.lib().mmtg_layernorm_bwd(_p(dy), int(dy.dtype == torch.bfloat16), _p(x), _p(mean), _p(rstd),
+                                             _p(gamma), _p(dx), int(accumulate), _p(dgamma), _p(dbeta), M, E,
+                                             _st()), "mmtg_layernorm_bwd")
+
+
+def colsum(x, out, copy16=None):
+    M, N = x.shape
+    _lib.check(_lib.lib().mmtg_colsum(_p(x), int(x.dtype == torch.bfloat16), C.c_int64(x.stride(0)), _p(copy16),
+                                      C.c_int64(copy16.stride(0) if copy16 is not None else 0), _p(out), M, N,
+                                      _st()), "mmtg_colsum")
+
+
+def attn_fwd(qkv, mask, B, L, NH):
+    E = NH * 64
+    out = torch.empty(B * L, E, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, NH, L, device=qkv.device)
+    _lib.check(_lib.lib().mmtg_attn_fwd(_p(qkv), _p(mask), _p(out), _p(lse), B, L, NH, _st()), "mmtg_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, mask, out, dout, lse, B, L, NH):
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, NH, L, device=qkv.device)
+    _lib.check(_lib.lib().mmtg_attn_bwd(_p(qkv), _p(mask), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, L,
+                                        NH, _st()), "mmtg_attn_bwd")
+    return dqkv
