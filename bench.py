@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py — MMTG hot-path benchmark (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload train|decode]
+
+One "step" = one pass of the training hot path over one synthetic batch of 32 samples per GPU:
+MMTG.forward + MyLoss + 0.2*KL, backward (with the bucketed NCCL gradient all-reduce when N > 1),
+global-norm clip and the AdamW update (restated src/train.py:188-197). Metric: train samples/s
+(BASELINE.json configs[1]; weak scaling: the per-GPU batch is fixed at 32).
+
+  value : device-timed (CUDA events, max over ranks) with the batch already resident in HBM
+  e2e   : the same step through the public Python surface with the batch in PINNED HOST memory,
+          host->device copies and the device->host loss read inside the timed region
+  roofline     : tensor bound for the dominant kernel (the tcgen05 GEMM), from per-launch CUDA
+                 events recorded by the library in extra, separately run, profiled steps
+  cpu_baseline : the CPU oracle's train step on the host cores (bounded sample)
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port:
+/root/reference does not exist on the GPU box) on the host cores and prints the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+TRAIN_GFLOP_PER_SAMPLE = 140.2  # BASELINE.md §3, L = 236
+PER_GPU_BATCH = 32
+ALPHA = 0.2
+STAGE = 3
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def summary(self):
+        self._stop_evt.set()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_train_step_time(batch_size, reps, threads):
+    """Restated reference train step (src/train.py:188-193) on the CPU oracle; returns s/step."""
+    from mmtg_b200 import synth
+    from mmtg_b200.configs import data_config
+    from oracle import mmtg_oracle as O
+    torch.set_num_threads(threads)
+    table = torch.from_numpy(synth.make_token_table())
+    sd = synth.make_state_dict(0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "decoder.gpt2.lm_head.weight"}
+    params["decoder.gpt2.lm_head.weight"] = params["decoder.gpt2.transformer.wte.weight"]
+    batch = synth.batch_to_torch(synth.make_batch(batch_size, seed=1234))
+    ts = []
+    for i in range(reps + 1):
+        for p in params.values():
+            p.grad = None
+        t0 = time.perf_counter()
+        hf, kl, logits = O.mmtg_forward(params, table, batch, data_config(), True)
+        total = O.my_loss(logits, batch["targets"], batch["rating"], STAGE).mean() + ALPHA * kl.mean()
+        total.backward()
+        if i > 0:  # first repetition is the warm-up
+            ts.append(time.perf_counter() - t0)
+    return float(np.median(ts))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    bs = 2
+    reps = max(1, min(args.steps, 5))
+    sec = cpu_train_step_time(bs, reps, threads)
+    val = bs / sec
+    line = {
+        "impl": "reference", "metric": "train samples/s", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": reps, "warmup": 1, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "MMTG train step fwd+bwd+curriculum negative loss, CPU fp32, bounded sample batch 2 (configs[1] shape per sample)"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{reps} timed steps of batch {bs} (L=236) after 1 warm-up, oracle/mmtg_oracle.py fwd+MyLoss+KL+autograd bwd"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mmtg_b200")
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from mmtg_b200 import _lib, synth
+    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200.loss import MyLoss
+    from mmtg_b200.model import MMTG
+    from mmtg_b200.optim import FusedAdamW
+    from mmtg_b200.parallel import GradSync
+
+    W = max(args.warmup, 3)
+    K = args.steps
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+
+    B = args.batch
+    table = synth.make_token_table()
+    model = MMTG(model_cfgs, data_config(), 13317, train_flag=True, token_table=table)
+    model.load_state_dict(synth.make_state_dict(0))  # identical replicas on every rank
+    model.to(dev)
+    if world > 1:
+        model.grad_sync = GradSync()
+    crit = MyLoss(data_config(), model_cfgs)
+    opt = FusedAdamW(model, lr=1e-5, max_grad_norm=1.0)
+    host = synth.batch_to_torch(synth.make_batch(B, seed=1234 + rank))
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    # L2 flush buffer (> 126 MB); the step's own working set (~3 GB of activations) already exceeds L2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(batch):
+        hf, kl, logits = model(batch)
+        loss = crit(logits, batch["targets"], batch["rating"], STAGE)
+        total = loss.mean() + ALPHA * kl.mean()
+        total.backward()
+        opt.step()
+        opt.zero_grad()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step(resident)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- device-timed, inputs resident ----
+    l0 = lib.mmtg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        step(resident)
+    e1.record()
+    barrier()
+    launches = int(lib.mmtg_launch_count() - l0)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss.item() ----
+    for _ in range(2):
+        step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}).item()
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(K):
+        batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        step(batch).item()
+    e3.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = torch.tensor([max(e2.elapsed_time(e3), e2e_wall * 1e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.summary()
+
+    # ---- roofline: per-launch CUDA events of the dominant kernel (tcgen05 GEMM), 2 extra steps ----
+    import ctypes as C
+    lib.mmtg_prof_reset()
+    lib.mmtg_prof_enable(1)
+    PROF_STEPS = 2
+    for _ in range(PROF_STEPS):
+        flush.zero_()
+        step(resident)
+    torch.cuda.synchronize()
+    lib.mmtg_prof_enable(0)
+    classes = {}
+    for cls, name in ((0, "gemm_tcgen05"), (1, "attention"), (2, "row_kernels")):
+        t, f, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        lib.mmtg_prof_collect(cls, C.byref(t), C.byref(f), C.byref(b), C.byref(n))
+        classes[name] = {"ms_per_step": t.value / PROF_STEPS, "launches_per_step": n.value // PROF_STEPS,
+                         "gflop_per_step": f.value / PROF_STEPS / 1e9, "gbytes_per_step": b.value / PROF_STEPS / 1e9}
+    lib.mmtg_prof_reset()
+    pk, pk_src = peaks()
+    gemm = classes["gemm_tcgen05"]
+    achieved = gemm["gflop_per_step"] / max(gemm["ms_per_step"], 1e-9)  # GFLOP/ms = TFLOP/s
+    peak = pk["bf16_tflops_sustained"]
+
+    global_batch = B * world
+    value = global_batch * K / (ms_total / 1e3)
+    e2e_value = global_batch * K / (e2e_ms.item() / 1e3)
+    if rank == 0:
+        line = {
+            "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "MMTG train step (fwd + MyLoss stage 3 + 0.2*KL, bwd, clip 1.0, AdamW) bf16 GEMMs / fp32 master+residual, batch 32 per GPU, L=236, V=13317 (BASELINE.json configs[1]); dropout p=0",
+                       "global_batch": global_batch, "seq_len": 236,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": "working set (~3 GB activations/step) exceeds L2; 256 MB flush before profiled steps"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms.item() / K},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of a step, CUDA events per launch)",
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk_src})",
+                         "step_model_flops_frac": (value / world) * TRAIN_GFLOP_PER_SAMPLE / 1e3 / peak},
+            "breakdown": classes,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sec = cpu_train_step_time(2, 3, threads)
+            line["cpu_baseline"] = {"value": 2 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "sample": "3 timed steps of batch 2 (L=236) after 1 warm-up, oracle/mmtg_oracle.py fwd+MyLoss+KL+autograd bwd, fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,11 @@ const char* mmtg_last_error(void);
 int mmtg_abi_version(void);
 /* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
 int64_t mmtg_launch_count(void);
+/* optional per-launch CUDA-event timing used by bench.py's roofline block.
+ * classes: 0 = tcgen05 GEMM, 1 = attention, 2 = row / reduction kernels */
+void mmtg_prof_enable(int32_t on);
+void mmtg_prof_reset(void);
+int mmtg_prof_collect(int32_t cls, double* ms, double* flops, double* bytes, int64_t* count);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05/TMEM fed by TMA:  out = epilogue(A · Bᵀ)
@@ -80,8 +85,8 @@ typedef struct mmtg_gemm_args {
   const int32_t* rowidx1;
   int64_t ldt1;
   float* colsum;
-  /* optional per-row (max, sum-exp) partials of the stored value over this tile's columns,
-   * layout [ceil(N/block_n)][M][2] fp32 — lets the loss kernels skip a full re-read of logits */
+  /* optional per-row (max, sum-exp) partials of the stored value over each HALF tile's columns,
+   * layout [2*ceil(N/block_n)][M][2] fp32 — lets the loss kernels skip a full re-read of logits */
   float* lse_partial;
   /* 0: dgelu_src holds the pre-activation u, value *= gelu_new'(u);
    * 1: dgelu_src holds a tanh OUTPUT y, value *= (1 - y*y)   (projector backward) */
@@ -201,6 +206,28 @@ int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, void* workspac
                         int64_t workspace_bytes, const float* g_kl, int32_t stage_begin,
                         int32_t stage_end, void* stream);
 int mmtg_dlogits_from_f32(const mmtg_dims* dims, void* workspace, const float* dlogits_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * KV-cached generation: the per-token body of sample_sequence (src/generate.py:117-142) and the
+ * decoder inference branch (src/model.py:291-326). A batch = independent batch-1 reference runs.
+ *   1. run mmtg_train_forward over [prompt | first token] (inference-branch type ids / masks);
+ *   2. mmtg_decode_load_prefix moves that prefix's K/V, fused context and key mask to the cache;
+ *   3. per position: mmtg_sample_rows decides gen[:, j+1] from the last logits and bumps the
+ *      device-side step index *j_ptr; mmtg_decode_step consumes gen[:, *j_ptr].
+ * gen: [B, gen_ld] int32 token ids (device). Everything is CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------ */
+int64_t mmtg_decode_workspace_bytes(const mmtg_dims* dims, int32_t Lmax);
+int mmtg_decode_load_prefix(const mmtg_dims* dims_prefix, void* train_workspace, int32_t Lmax,
+                            void* decode_workspace, const int32_t* prefix_mask, void* stream);
+int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_workspace, const int32_t* gen,
+                     int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
+                     float* logits, void* stream);
+/* ban_specials: set ids 1, 2, 100, 102 to -inf (src/generate.py:133-136).
+ * dbg_probs (optional): [B, 1024, 2] (kept token id, probability) of the filtered distribution */
+int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_ld, int32_t* j_ptr,
+                     int32_t B, int32_t V, int32_t sent_len, float temperature, int32_t top_k,
+                     float top_p, float rep_penalty, uint64_t seed, int32_t ban_specials,
+                     float* dbg_probs, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer step over the flat buffers: clip_grad_norm_ (src/train.py:194) and

@@ -508,6 +508,8 @@ int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, in
   p.qkv = qkv; p.kmask = kmask; p.out = out; p.lse = lse;
   p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
   dim3 grid(cdiv(L, BQ), B * NH);
+  // causal FLOPs: 2 GEMMs x 2 x 64 x L(L+1)/2 per (b, h)
+  ProfScope prof(1, 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 4 * B * L * NH * 64, st);
   attn_fwd_kernel<<<grid, ATT_THREADS, 0, st>>>(p);
   MMTG_LAUNCH_OK();
   count_launch();
@@ -519,6 +521,7 @@ int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dou
   AttnParams p{};
   p.qkv = qkv; p.kmask = kmask; p.lse = const_cast<float*>(lse); p.dout = dout; p.delta = delta;
   p.dqkv = dqkv; p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
+  ProfScope prof(1, 2.5 * 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 8 * B * L * NH * 64, st);
   const long long warps = (long long)B * L * NH;
   attn_delta_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, st>>>(out, dout, delta, B, L, NH, p.E);
   MMTG_LAUNCH_OK();

@@ -1,0 +1,517 @@
+// KV-cached autoregressive decoding for MMTG generation (src/generate.py:97-145).
+//
+// The reference re-runs the whole model on the whole prefix for every token (no KV cache,
+// batch 1). Every per-position input of its inference branch (token, fused context k = j/44,
+// position, type id, key mask; src/model.py:291-326) depends only on tokens <= j, so caching
+// K/V per layer is semantically exact. A batch of B rows here is B independent batch-1
+// reference runs (the reference derives type ids / masks from row 0 only).
+//
+// Per step (one new token per row):  prep (embedding + type/mask rules) -> projector GEMMs ->
+// 12 x [LN, c_attn GEMM, cached attention, c_proj GEMM(+res), LN, c_fc GEMM(gelu), c_proj GEMM
+// (+res)] -> ln_f -> lm_head GEMM -> fused sampler (repetition penalty, temperature, bans,
+// forced [#EOS#]/[#START#], PAD continuation, top-k, top-p, multinomial). The step index lives
+// in device memory so the whole step is CUDA-graph capturable and replayable.
+#include <string.h>
+
+#include "../../include/mmtg_b200.h"
+#include "ops.h"
+
+namespace mmtg {
+
+void count_launch(int n = 1);
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct DWs {
+  bf16 *kcache, *vcache;  // [NL][B][NH][Lmax][64]
+  float* ctx;             // [S*B, Dw]
+  int* keymask;           // [B, Lmax]
+  int* types;             // [B]
+  int* posidx;            // [B]
+  bf16 *emb16, *p1, *x16, *qkv16, *att16, *a16;
+  float *h, *h2;
+  size_t bytes;
+};
+
+void carve_decode(const mmtg_dims& d, int Lmax, uint8_t* base, DWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t B = d.B, E = d.E;
+  const size_t cache = (size_t)d.NL * B * d.NH * Lmax * 64;
+  w->kcache = (bf16*)take(cache * 2);
+  w->vcache = (bf16*)take(cache * 2);
+  w->ctx = (float*)take((size_t)d.S * B * d.Dw * 4);
+  w->keymask = (int*)take(B * Lmax * 4);
+  w->types = (int*)take(B * 4);
+  w->posidx = (int*)take(B * 4);
+  w->emb16 = (bf16*)take(B * d.Dw * 2);
+  w->p1 = (bf16*)take(B * d.He * 2);
+  w->x16 = (bf16*)take(B * E * 2);
+  w->qkv16 = (bf16*)take(B * 3 * E * 2);
+  w->att16 = (bf16*)take(B * E * 2);
+  w->a16 = (bf16*)take(B * 4 * E * 2);
+  w->h = (float*)take(B * E * 4);
+  w->h2 = (float*)take(B * E * 4);
+  w->bytes = off;
+}
+
+// Per row: embedding of the new token (+ fused context of its sentence pair), inference-branch
+// type id (src/model.py:300-306) and key mask (:309-312), absolute position.
+__global__ void __launch_bounds__(256)
+decode_prep_kernel(const int* __restrict__ gen, int gen_ld, const int* __restrict__ j_ptr,
+                   const float* __restrict__ table, const float* __restrict__ ctx,
+                   bf16* __restrict__ emb16, int* __restrict__ types, int* __restrict__ posidx,
+                   int* __restrict__ keymask, int B, int P, int S, int sent_len, int n_sent, int D,
+                   int Lmax) {
+  const int b = blockIdx.x;
+  const int j = *j_ptr;
+  const int tok = gen[b * gen_ld + j];
+  if (threadIdx.x == 0) {
+    int ty;
+    const int r = (j + 1) % sent_len;
+    if (r == 0 || r == 1 || tok == 0) {
+      ty = 0;
+    } else {
+      const int s = j / sent_len;  // type list [1..n_sent, 1]
+      ty = s < n_sent ? s + 1 : 1;
+    }
+    types[b] = ty;
+    posidx[b] = P + j;
+    keymask[b * Lmax + P + j] = tok != 0 ? 1 : 0;
+  }
+  const int k = j / (2 * sent_len);
+  const float* trow = table + (long long)tok * D;
+  const float* crow = k < S ? ctx + ((long long)k * B + b) * D : nullptr;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(trow + c));
+    if (crow) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(crow + c));
+      a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+    *reinterpret_cast<uint2*>(emb16 + (long long)b * D + c) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
+// One warp per (row, head): append this step's K/V to the cache, then attend over keys 0..pos
+// with the key-padding mask. Scores live in shared memory (any context length).
+__global__ void __launch_bounds__(128)
+decode_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc,
+                   const int* __restrict__ keymask, const int* __restrict__ j_ptr,
+                   bf16* __restrict__ out, int B, int NH, int P, int Lmax) {
+  extern __shared__ float s_scores[];  // [4 warps][Lmax]
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= B * NH) return;
+  const int b = w / NH, h = w - b * NH, l = lane_id();
+  const int pos = P + *j_ptr;
+  const int E = NH * 64;
+  float* sc = s_scores + (threadIdx.x >> 5) * Lmax;
+  const bf16* row = qkv + (long long)b * 3 * E + h * 64;
+  bf16* kbase = kc + ((long long)b * NH + h) * Lmax * 64;
+  bf16* vbase = vc + ((long long)b * NH + h) * Lmax * 64;
+  // append
+  reinterpret_cast<uint32_t*>(kbase + (long long)pos * 64)[l] = reinterpret_cast<const uint32_t*>(row + E)[l];
+  reinterpret_cast<uint32_t*>(vbase + (long long)pos * 64)[l] = reinterpret_cast<const uint32_t*>(row + 2 * E)[l];
+  __syncwarp();
+  // q in registers (all 64 dims per lane, as fp32)
+  float q[64];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + i * 8);
+    const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[e]));
+      q[i * 8 + 2 * e] = f.x;
+      q[i * 8 + 2 * e + 1] = f.y;
+    }
+  }
+  float mx = -INFINITY;
+  for (int key = l; key <= pos; key += 32) {
+    float d = -INFINITY;
+    if (keymask[b * Lmax + key] != 0) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)key * 64);
+      d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = kr[i];
+        const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[e]));
+          d += q[i * 8 + 2 * e] * f.x + q[i * 8 + 2 * e + 1] * f.y;
+        }
+      }
+      d *= 0.125f;
+    }
+    sc[key] = d;
+    mx = fmaxf(mx, d);
+  }
+  mx = warp_max(mx);
+  if (mx == -INFINITY) mx = 0.f;
+  float sum = 0.f;
+  for (int key = l; key <= pos; key += 32) {
+    const float e = __expf(sc[key] - mx);
+    sc[key] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int key = 0; key <= pos; ++key) {
+    const float pj = sc[key];
+    if (pj != 0.f) {
+      const float2 v = __bfloat1622float2(
+          reinterpret_cast<const __nv_bfloat162*>(vbase + (long long)key * 64)[l]);
+      acc.x += pj * v.x;
+      acc.y += pj * v.y;
+    }
+  }
+  reinterpret_cast<__nv_bfloat162*>(out + (long long)b * E + h * 64)[l] =
+      __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
+}
+
+// Copy the prefix K/V produced by the training-style prefill forward ([B*Lp, 3E] per layer) into
+// the cache. grid = (B*Lp, NH), 32 threads.
+__global__ void kv_scatter_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
+                                  bf16* __restrict__ vc, int B, int Lp, int NH, int Lmax) {
+  const int row = blockIdx.x, h = blockIdx.y, l = threadIdx.x;
+  const int b = row / Lp, pos = row - b * Lp;
+  const int E = NH * 64;
+  const bf16* src = qkv + (long long)row * 3 * E + h * 64;
+  const long long dst = (((long long)b * NH + h) * Lmax + pos) * 64;
+  reinterpret_cast<uint32_t*>(kc + dst)[l] = reinterpret_cast<const uint32_t*>(src + E)[l];
+  reinterpret_cast<uint32_t*>(vc + dst)[l] = reinterpret_cast<const uint32_t*>(src + 2 * E)[l];
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused sampler, one 1024-thread block per row (src/generate.py:118-142 + 64-94).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax argmax_merge(ArgMax a, ArgMax b) {
+  // larger value wins; ties -> smaller index (deterministic)
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ ArgMax block_argmax(const float* s, int V, ArgMax* red) {
+  ArgMax m{-INFINITY, 0x7fffffff};
+  for (int c = threadIdx.x; c < V; c += blockDim.x) m = argmax_merge(m, ArgMax{s[c], c});
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax t{__shfl_xor_sync(0xffffffffu, m.v, o), __shfl_xor_sync(0xffffffffu, m.i, o)};
+    m = argmax_merge(m, t);
+  }
+  if (lane_id() == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ArgMax t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : ArgMax{-INFINITY, 0x7fffffff};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMax u{__shfl_xor_sync(0xffffffffu, t.v, o), __shfl_xor_sync(0xffffffffu, t.i, o)};
+      t = argmax_merge(t, u);
+    }
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const ArgMax r = red[0];
+  __syncthreads();
+  return r;
+}
+
+constexpr int MAX_SURV = 1024;
+
+__global__ void __launch_bounds__(1024)
+sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ gen, int gen_ld,
+                   int* __restrict__ j_ptr, int ban_specials, int V, int sent_len, float temperature,
+                   int top_k, float top_p, float rep_penalty, unsigned long long seed,
+                   float* __restrict__ dbg_probs) {
+  extern __shared__ float s[];  // [V] working logits
+  __shared__ ArgMax red[32];
+  __shared__ float sv[MAX_SURV];
+  __shared__ int si[MAX_SURV];
+  __shared__ int s_n;
+  const int b = blockIdx.x;
+  const int i = *j_ptr;  // reference loop index: decides token at position i + 1
+  int* g = gen + (long long)b * gen_ld;
+  int next = -1;
+  if (i > 0 && (i + 2) % sent_len == 0) next = 2;        // forced [#EOS#]   (generate.py:118-120)
+  else if (i > 0 && (i + 2) % sent_len == 1) next = 1;   // forced [#START#] (generate.py:121-123)
+  else if (g[i] == 0) next = 0;                          // PAD continuation (generate.py:137-138)
+  if (next < 0) {
+    const float* z = logits + (long long)b * ld;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) s[c] = z[c];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // repetition penalty: plain division, once per OCCURRENCE, ids 0 and 102 exempt
+      if (rep_penalty != 1.0f)
+        for (int t = 0; t <= i; ++t) {
+          const int id = g[t];
+          if (id != 0 && id != 102 && id < V) s[id] = s[id] / rep_penalty;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < V; c += blockDim.x) s[c] = s[c] / temperature;
+    __syncthreads();
+    if (threadIdx.x == 0 && ban_specials) {
+      s[1] = -INFINITY; s[2] = -INFINITY; s[100] = -INFINITY; s[102] = -INFINITY;
+    }
+    __syncthreads();
+    // full-vocabulary softmax normaliser is only needed for pure top-p (top_k == 0)
+    float lse_all = 0.f;
+    if (top_k <= 0 && top_p > 0.f) {
+      ArgMax m = block_argmax(s, V, red);
+      float a = 0.f;
+      for (int c = threadIdx.x; c < V; c += blockDim.x) a += __expf(s[c] - m.v);
+      a = warp_sum(a);
+      if (lane_id() == 0) sv[threadIdx.x >> 5] = a;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += sv[w2];
+        sv[0] = m.v + logf(t);
+      }
+      __syncthreads();
+      lse_all = sv[0];
+      __syncthreads();
+    }
+    // descending selection of survivors
+    int n = 0;
+    float cum = 0.f, kth = -INFINITY;
+    const int kk = top_k > 0 ? min(top_k, V) : 0;
+    while (n < MAX_SURV) {
+      const ArgMax m = block_argmax(s, V, red);
+      if (m.v == -INFINITY) break;
+      if (kk > 0) {
+        if (n >= kk && m.v < kth) break;  // beyond the k-th value (ties at the k-th are kept)
+        if (n == kk - 1) kth = m.v;
+      } else if (top_p > 0.f) {
+        // pure nucleus: stop once the PRECEDING cumulative probability exceeds p
+        if (n > 0 && cum > top_p) break;
+        cum += __expf(m.v - lse_all);
+      } else {
+        break;  // neither filter (k = 0, p = 0): full-vocabulary multinomial below
+      }
+      if (threadIdx.x == 0) {
+        sv[n] = m.v;
+        si[n] = m.i;
+        s[m.i] = -INFINITY;
+      }
+      __syncthreads();
+      ++n;
+    }
+    if (n == 0 && kk == 0 && top_p <= 0.f) {
+      // plain softmax sampling over the whole (banned-id filtered) vocabulary
+      const ArgMax m = block_argmax(s, V, red);
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int c = 0; c < V; ++c) t += __expf(s[c] - m.v);
+        const uint64_t r = splitmix64(seed ^ splitmix64(((uint64_t)b << 32) | (uint32_t)i));
+        const float u = (float)(r >> 40) * (1.0f / 16777216.0f) * t;
+        float c2 = 0.f;
+        int pick = m.i;
+        for (int c = 0; c < V; ++c) {
+          c2 += __expf(s[c] - m.v);
+          if (u < c2) {
+            pick = c;
+            break;
+          }
+        }
+        s_n = pick;
+      }
+    } else if (threadIdx.x == 0) {
+      int keep = n;
+      if (kk > 0 && top_p > 0.f) {
+        // nucleus over the top-k survivors (softmax over survivors only: the rest are -inf)
+        float t = 0.f;
+        for (int c = 0; c < n; ++c) t += __expf(sv[c] - sv[0]);
+        float c2 = 0.f;
+        keep = 0;
+        for (int c = 0; c < n; ++c) {
+          if (c > 0 && c2 > top_p) break;
+          c2 += __expf(sv[c] - sv[0]) / t;
+          ++keep;
+        }
+      }
+      // multinomial over the kept survivors
+      float t = 0.f;
+      for (int c = 0; c < keep; ++c) t += __expf(sv[c] - sv[0]);
+      const uint64_t r = splitmix64(seed ^ splitmix64(((uint64_t)b << 32) | (uint32_t)i));
+      const float u = (float)(r >> 40) * (1.0f / 16777216.0f) * t;
+      float c2 = 0.f;
+      int pick = keep > 0 ? si[keep - 1] : 0;
+      for (int c = 0; c < keep; ++c) {
+        c2 += __expf(sv[c] - sv[0]);
+        if (u < c2) {
+          pick = si[c];
+          break;
+        }
+      }
+      s_n = pick;
+      if (dbg_probs) {  // test hook: kept ids and their probabilities
+        float* d = dbg_probs + (long long)b * 2 * MAX_SURV;
+        for (int c = 0; c < MAX_SURV; ++c) {
+          d[2 * c] = c < keep ? (float)si[c] : -1.f;
+          d[2 * c + 1] = c < keep ? __expf(sv[c] - sv[0]) / t : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    next = s_n;
+  }
+  if (threadIdx.x == 0) g[i + 1] = next;
+  // the shared step index is advanced by a separate 1-thread kernel (advance_kernel): doing it
+  // here would need a grid-wide barrier
+}
+
+__global__ void advance_kernel(int* j_ptr) { *j_ptr += 1; }
+
+}  // namespace
+}  // namespace mmtg
+
+using namespace mmtg;
+
+extern "C" int64_t mmtg_decode_workspace_bytes(const mmtg_dims* dims, int32_t Lmax) {
+  if (!dims || Lmax <= 0) return -1;
+  DWs w;
+  carve_decode(*dims, Lmax, nullptr, &w);
+  return (int64_t)w.bytes;
+}
+
+namespace mmtg {
+namespace {
+__global__ void keymask_init_kernel(const int* __restrict__ prefix_mask, int* __restrict__ keymask,
+                                    int B, int Lp, int Lmax) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Lmax) return;
+  const int b = idx / Lmax, p = idx - b * Lmax;
+  keymask[idx] = p < Lp ? prefix_mask[b * Lp + p] : 0;
+}
+}  // namespace
+
+// After a training-style forward over the prefix (prompt + first token; Lp = d.L), move the
+// prefix K/V of every layer, the fused context and the prefix key mask into the decode workspace.
+int decode_load_prefix(const mmtg_dims& d, const bf16* const* qkv_layers, const float* ctx_out,
+                       int Lmax, void* decode_ws, const int* prefix_mask, cudaStream_t st) {
+  MMTG_CHECK_ARG(d.L <= Lmax, "prefix longer than the cache");
+  DWs w;
+  carve_decode(d, Lmax, (uint8_t*)decode_ws, &w);
+  const size_t layer_cache = (size_t)d.B * d.NH * Lmax * 64;
+  for (int l = 0; l < d.NL; ++l) {
+    dim3 grid(d.B * d.L, d.NH);
+    kv_scatter_kernel<<<grid, 32, 0, st>>>(qkv_layers[l], w.kcache + l * layer_cache,
+                                           w.vcache + l * layer_cache, d.B, d.L, d.NH, Lmax);
+    MMTG_LAUNCH_OK();
+  }
+  MMTG_CUDA_OK(cudaMemcpyAsync(w.ctx, ctx_out, (size_t)d.S * d.B * d.Dw * 4, cudaMemcpyDeviceToDevice, st));
+  keymask_init_kernel<<<cdiv(d.B * Lmax, 256), 256, 0, st>>>(prefix_mask, w.keymask, d.B, d.L, Lmax);
+  MMTG_LAUNCH_OK();
+  count_launch(d.NL + 1);
+  return 0;
+}
+}  // namespace mmtg
+
+extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_ws, const int32_t* gen,
+                                int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
+                                float* logits, void* stream) {
+  MMTG_CHECK_ARG(m && decode_ws && gen && j_ptr && logits, "null argument");
+  const mmtg_dims& d = m->dims;
+  DWs w;
+  carve_decode(d, Lmax, (uint8_t*)decode_ws, &w);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* P = m->params;
+  const bf16* W = (const bf16*)m->params_bf16;
+  const mmtg_param_offsets& o = m->off;
+  const int B = d.B, E = d.E, He = d.He, Dw = d.Dw;
+  const float eps = 1e-5f;
+  decode_prep_kernel<<<B, 256, 0, st>>>(gen, gen_ld, j_ptr, m->token_table, w.ctx, w.emb16, w.types,
+                                        w.posidx, w.keymask, B, d.P, d.S, sent_len, n_sent, Dw, Lmax);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  auto gemm = [&](const bf16* A, long long lda, const bf16* Bm, long long ldb, bool b_mn, int N, int K) {
+    mmtg_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.lda = lda; a.B = Bm; a.ldb = ldb; a.b_mn_major = b_mn;
+    a.M = B; a.N = N; a.K = K; a.block_n = 128;
+    return a;
+  };
+  {
+    mmtg_gemm_args a = gemm(w.emb16, Dw, W + o.proj1_w, Dw, false, He, Dw);
+    a.out = w.p1; a.ldo = He; a.out_dtype = MMTG_BF16; a.bias = P + o.proj1_b; a.act = MMTG_ACT_TANH;
+    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    a = gemm(w.p1, He, W + o.proj2_w, He, false, E, He);
+    a.out = w.h; a.ldo = E; a.out_dtype = MMTG_F32; a.bias = P + o.proj2_b;
+    a.rowtab0 = P + o.wpe; a.ldt0 = E; a.rowidx0 = w.posidx;
+    a.rowtab1 = P + o.wte; a.ldt1 = E; a.rowidx1 = w.types;
+    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+  }
+  const size_t layer_cache = (size_t)B * d.NH * Lmax * 64;
+  const int att_smem = 4 * Lmax * 4;
+  for (int l = 0; l < d.NL; ++l) {
+    const mmtg_layer_offsets& lo = o.layer[l];
+    MMTG_TRY(layernorm_fwd(w.h, P + lo.ln1_w, P + lo.ln1_b, w.x16, nullptr, nullptr, nullptr, B, E, eps, st));
+    mmtg_gemm_args a = gemm(w.x16, E, W + lo.attn_w, 3 * E, true, 3 * E, E);
+    a.out = w.qkv16; a.ldo = 3 * E; a.out_dtype = MMTG_BF16; a.bias = P + lo.attn_b;
+    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    decode_attn_kernel<<<cdiv(B * d.NH, 4), 128, att_smem, st>>>(
+        w.qkv16, w.kcache + l * layer_cache, w.vcache + l * layer_cache, w.keymask, j_ptr, w.att16, B, d.NH,
+        d.P, Lmax);
+    MMTG_LAUNCH_OK();
+    count_launch();
+    a = gemm(w.att16, E, W + lo.proj_w, E, true, E, E);
+    a.out = w.h2; a.ldo = E; a.out_dtype = MMTG_F32; a.bias = P + lo.proj_b; a.residual = w.h; a.ldr = E;
+    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    MMTG_TRY(layernorm_fwd(w.h2, P + lo.ln2_w, P + lo.ln2_b, w.x16, nullptr, nullptr, nullptr, B, E, eps, st));
+    a = gemm(w.x16, E, W + lo.fc_w, 4 * E, true, 4 * E, E);
+    a.out = w.a16; a.ldo = 4 * E; a.out_dtype = MMTG_BF16; a.bias = P + lo.fc_b; a.act = MMTG_ACT_GELU_NEW;
+    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    a = gemm(w.a16, 4 * E, W + lo.proj2_w, E, true, E, 4 * E);
+    a.out = w.h; a.ldo = E; a.out_dtype = MMTG_F32; a.bias = P + lo.proj2_b; a.residual = w.h2; a.ldr = E;
+    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+  }
+  MMTG_TRY(layernorm_fwd(w.h, P + o.lnf_w, P + o.lnf_b, w.x16, nullptr, nullptr, nullptr, B, E, eps, st));
+  mmtg_gemm_args a = gemm(w.x16, E, W + o.wte, E, false, d.V, E);
+  a.out = logits; a.ldo = d.V; a.out_dtype = MMTG_F32;
+  MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+  return 0;
+}
+
+extern "C" int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_ld,
+                                int32_t* j_ptr, int32_t B, int32_t V, int32_t sent_len,
+                                float temperature, int32_t top_k, float top_p, float rep_penalty,
+                                uint64_t seed, int32_t ban_specials, float* dbg_probs, void* stream) {
+  MMTG_CHECK_ARG(logits && gen && j_ptr && B > 0 && V > 102 && temperature > 0.f, "bad sampler args");
+  MMTG_CHECK_ARG(top_k <= MAX_SURV, "top_k > %d not supported", MAX_SURV);
+  static bool attr_set = false;
+  const int smem = V * 4;
+  if (!attr_set) {
+    MMTG_CUDA_OK(cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  MMTG_CHECK_ARG(smem <= 96 * 1024, "vocabulary too large for the sampler's shared-memory copy");
+  cudaStream_t st = (cudaStream_t)stream;
+  sample_rows_kernel<<<B, 1024, smem, st>>>(logits, ld, gen, gen_ld, j_ptr, ban_specials, V, sent_len, temperature,
+                                            top_k, top_p, rep_penalty, (unsigned long long)seed, dbg_probs);
+  MMTG_LAUNCH_OK();
+  advance_kernel<<<1, 1, 0, st>>>(j_ptr);
+  MMTG_LAUNCH_OK();
+  count_launch(2);
+  return 0;
+}

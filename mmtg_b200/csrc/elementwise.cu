@@ -328,6 +328,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y
                   float* mean, float* rstd, int M, int E, float eps, cudaStream_t st) {
   MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
   const int blocks = min(cdiv(M, 8), num_sms() * 8);
+  ProfScope prof(2, 0, (double)M * E * (4 + (y16 ? 2 : 0) + (y32 ? 4 : 0)), st);
   if (E == 768) ln_fwd_kernel<768><<<blocks, 256, 0, st>>>(x, gamma, beta, y16, y32, mean, rstd, M, eps);
   else ln_fwd_kernel<512><<<blocks, 256, 0, st>>>(x, gamma, beta, y16, y32, mean, rstd, M, eps);
   MMTG_LAUNCH_OK();
@@ -340,6 +341,7 @@ int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean
                   int M, int E, cudaStream_t st) {
   MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
   const int blocks = min(cdiv(M, 8), num_sms() * 2);
+  ProfScope prof(2, 0, (double)M * E * (4 + (dy_bf16 ? 2 : 4) + 4 + (accumulate_dx ? 4 : 0)), st);
 #define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, M)
   if (E == 768) { if (dy_bf16) LNB(768, true); else LNB(768, false); }
   else { if (dy_bf16) LNB(512, true); else LNB(512, false); }
@@ -365,6 +367,7 @@ int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc,
   int splits = cdiv(num_sms() * 4, cdiv(N, 64));
   splits = max(1, min(splits, cdiv(M, 32)));
   dim3 grid(cdiv(N, 64), splits);
+  ProfScope prof(2, 0, (double)M * N * ((x_bf16 ? 2 : 4) + (copy16 ? 2 : 0)), st);
   if (x_bf16) colsum_kernel<true><<<grid, 256, 0, st>>>(x, ld, nullptr, 0, out, M, N);
   else colsum_kernel<false><<<grid, 256, 0, st>>>(x, ld, copy16, ldc, out, M, N);
   MMTG_LAUNCH_OK();
@@ -375,6 +378,7 @@ int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc,
 int embed_fwd(const float* table, const int* topic_ids, const int* input_ids, const float* ctx,
               bf16* out, int B, int P, int T, int S, int two_sent, int D, cudaStream_t st) {
   MMTG_CHECK_ARG(D % 8 == 0, "embedding width must be a multiple of 8");
+  ProfScope prof(2, 0, (double)B * (P + T) * D * 6, st);
   embed_fwd_kernel<<<B * (P + T), 256, 0, st>>>(table, topic_ids, input_ids, ctx, out, B, P, T, S, two_sent, D);
   MMTG_LAUNCH_OK();
   count_launch();

@@ -119,7 +119,7 @@ void carve(const mmtg_dims& d, uint8_t* base, Ws* w) {
   w->xf = b16(M * E);
   w->meanf = f32(M);
   w->rstdf = f32(M);
-  const size_t nt = (size_t)cdiv(d.V, 128);  // enough for either tile width
+  const size_t nt = (size_t)2 * cdiv(d.V, 128);  // half-tile partial slots, either tile width
   w->lse_part = f32(nt * M * 2);
   w->lse = f32(M);
   w->hf_sum = f32(d.B);
@@ -174,7 +174,7 @@ void carve(const mmtg_dims& d, uint8_t* base, Ws* w) {
 }
 
 int check_dims(const mmtg_dims& d) {
-  MMTG_CHECK_ARG(d.B > 0 && d.L == d.P + d.T && d.T > 1, "bad dims B=%d P=%d T=%d L=%d", d.B, d.P, d.T, d.L);
+  MMTG_CHECK_ARG(d.B > 0 && d.L == d.P + d.T && d.T >= 1, "bad dims B=%d P=%d T=%d L=%d", d.B, d.P, d.T, d.L);
   MMTG_CHECK_ARG(d.NL > 0 && d.NL <= MMTG_MAX_LAYERS, "n_layer %d out of range", d.NL);
   MMTG_CHECK_ARG(d.E == d.NH * 64, "head_dim must be 64 (E=%d NH=%d)", d.E, d.NH);
   MMTG_CHECK_ARG(d.Vp >= d.V && d.Vp % 8 == 0, "Vp must be V rounded up to a multiple of 8");
@@ -252,6 +252,21 @@ extern "C" int mmtg_dlogits_from_f32(const mmtg_dims* dims, void* workspace, con
   Ws w;
   carve(*dims, (uint8_t*)workspace, &w);
   return dlogits_f32_to_bf16(src, w.dlogits16, dims->B * dims->L, dims->V, dims->Vp, (cudaStream_t)stream);
+}
+
+namespace mmtg {
+int decode_load_prefix(const mmtg_dims& d, const bf16* const* qkv_layers, const float* ctx_out,
+                       int Lmax, void* decode_ws, const int* prefix_mask, cudaStream_t st);
+}
+extern "C" int mmtg_decode_load_prefix(const mmtg_dims* dp, void* train_ws, int32_t Lmax,
+                                       void* decode_ws, const int32_t* prefix_mask, void* stream) {
+  MMTG_CHECK_ARG(dp && train_ws && decode_ws && prefix_mask, "null argument");
+  MMTG_TRY(check_dims(*dp));
+  Ws w;
+  carve(*dp, (uint8_t*)train_ws, &w);
+  const bf16* qkv[MMTG_MAX_LAYERS];
+  for (int l = 0; l < dp->NL; ++l) qkv[l] = w.layer[l].qkv;
+  return decode_load_prefix(*dp, qkv, w.ctx_out, Lmax, decode_ws, prefix_mask, (cudaStream_t)stream);
 }
 
 extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
@@ -346,7 +361,7 @@ extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void
   MMTG_TRY(layernorm_fwd(h_last, P + o.lnf_w, P + o.lnf_b, w.xf, nullptr, w.meanf, w.rstdf, M, E, eps, st));
   const int bn = 256;
   MMTG_TRY(Gemm(w.xf, E, false, W + o.wte, E, false, M, d.V, E).out_f32(logits, d.V).lse(w.lse_part, bn).run(st));
-  MMTG_TRY(lse_combine(w.lse_part, w.lse, M, cdiv(d.V, bn), st));
+  MMTG_TRY(lse_combine(w.lse_part, w.lse, M, 2 * cdiv(d.V, bn), st));
   MMTG_TRY(ce_reduce(logits, d.V, w.lse, b->topic_ids, b->targets, w.hf_sum, nullptr, scalars_out, B,
                      d.L, d.P, d.T, st));
   return 0;

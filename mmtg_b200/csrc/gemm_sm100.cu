@@ -4,9 +4,13 @@
 // and wgrad) — see include/mmtg_b200.h for the reference call sites.
 //
 // Design (B200-first, not a translation of anything in the reference, which has no kernels):
-//  * persistent CTAs (one per SM), static round-robin over (tile, k-split) work units;
+//  * persistent CTAs (one per SM) in clusters of 2: the pair works on two vertically adjacent
+//    128-row tiles of the same column block, so the B tile is fetched ONCE per pair — each CTA
+//    loads half of it and TMA-multicasts it into both CTAs' shared memory (the mainloop is
+//    L2-bandwidth bound otherwise: 48 KB per CTA per k-block -> 32 KB);
+//  * static round-robin of the clusters over (tile pair, k-split) work units;
 //  * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma
-//    issuer, warps 2..5 = epilogue (one TMEM lane quadrant each);
+//    issuer, warps 2..9 = epilogue (two per TMEM lane quadrant, half the tile's columns each);
 //  * operands staged by TMA into a multi-stage SWIZZLE_128B shared-memory ring; both K-major
 //    and MN-major operand layouts are consumed straight from HBM (no transposes for wgrad);
 //  * fp32 accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile i
@@ -15,6 +19,7 @@
 //    fused bias / tanh / gelu_new / dgelu / residual / row-gather adds / column sums / split-K
 //    atomics / per-row log-sum-exp partials.
 #include <mutex>
+#include <string.h>
 #include <unordered_map>
 
 #include "../../include/mmtg_b200.h"
@@ -24,7 +29,7 @@ namespace mmtg {
 
 struct GemmParams {
   int M, N, K;
-  int num_m, num_n, num_kb, kb_per_split, splits;
+  int num_m, num_mp, num_n, num_kb, kb_per_split, splits;
   int a_mn, b_mn;
   // epilogue
   void* out;
@@ -60,17 +65,17 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int EPI_PITCH = 36;  // floats; 16-B aligned rows, conflict-free
+  static constexpr int EPI_PITCH = 32;  // floats; XOR-swizzled 16-B chunks, no padding
   static constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH;
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_FLOATS * 4;
+  static constexpr int EPI_BYTES = 8 * EPI_WARP_FLOATS * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
-  static constexpr int THREADS = 192;
+  static constexpr int THREADS = 320;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using C = GemmCfg<BN>;
@@ -90,11 +95,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 2);  // MMA commits of both CTAs of the pair (multicast arrivals)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);
     }
     fence_barrier_init();
   }
@@ -108,18 +113,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // peer barriers must be initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total = p.num_m * p.num_n * p.splits;
+  const uint32_t crank = cluster_ctarank();       // 0 / 1 within the pair
+  const int cluster_id = blockIdx.x >> 1;
+  const int nclusters = gridDim.x >> 1;
+  const int total = p.num_mp * p.num_n * p.splits;  // work units of a PAIR
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int s = 0;
     uint32_t ph = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int w = cluster_id; w < total; w += nclusters) {
       const int tile = w / p.splits, ks = w - tile * p.splits;
-      const int n_t = tile / p.num_m, m_t = tile - n_t * p.num_m;
+      const int n_t = tile / p.num_mp, m_t = (tile - n_t * p.num_mp) * 2 + (int)crank;
       const int m0 = m_t * C::BM, n0 = n_t * BN;
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -128,6 +137,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (lane == 0) {
           uint8_t* sA = smem + s * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
+          // A tile (own) + the whole B tile: half from this CTA, half multicast by the peer
           mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
           if (!p.a_mn) {
             tma_load_2d(sA, &tmA, &full[s], kb * C::BK, m0);
@@ -136,12 +146,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int j = 0; j < C::BM / 64; ++j)
               tma_load_2d(sA + j * 8192, &tmA, &full[s], m0 + 64 * j, kb * C::BK);
           }
-          if (!p.b_mn) {
-            tma_load_2d(sB, &tmB, &full[s], kb * C::BK, n0);
+          if (!p.b_mn) {  // rows [crank*BN/2, +BN/2) of the B tile -> both CTAs
+            tma_load_2d_mc(sB + crank * (C::B_BYTES / 2), &tmB, &full[s], kb * C::BK,
+                           n0 + (int)crank * (BN / 2), (uint16_t)3);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sB + j * 8192, &tmB, &full[s], n0 + 64 * j, kb * C::BK);
+            for (int j = 0; j < BN / 128; ++j) {
+              const int jj = (int)crank * (BN / 128) + j;
+              tma_load_2d_mc(sB + jj * 8192, &tmB, &full[s], n0 + 64 * jj, kb * C::BK, (uint16_t)3);
+            }
           }
         }
         __syncwarp();
@@ -163,7 +176,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     uint32_t ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int w = cluster_id; w < total; w += nclusters) {
       const int tile = w / p.splits, ks = w - tile * p.splits;
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -182,7 +195,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             const uint64_t bd = umma_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024u);
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot in BOTH CTAs (each producer multicasts into the other's stage)
+          umma_commit_mc(&empty[s], (uint16_t)3);
         }
         __syncwarp();
         if (++s == C::STAGES) {
@@ -198,26 +212,78 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    // Two warps per TMEM lane quadrant: warps 2..5 own the left half of the tile's columns,
+    // warps 6..9 the right half (a warp may only touch lanes 32*(warp%4) .. +31).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NCH = BN / 64;  // 32-column chunks per warp
     float* epi = epi_all + (warp - 2) * C::EPI_WARP_FLOATS;
+    const int rs = lane >> 3, cg = lane & 7;  // vector mapping: row sub-index, 4-column group
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int w = cluster_id; w < total; w += nclusters) {
       const int tile = w / p.splits;
-      const int n_t = tile / p.num_m, m_t = tile - n_t * p.num_m;
-      const int m0 = m_t * C::BM, n0 = n_t * BN;
+      const int n_t = tile / p.num_mp, m_t = (tile - n_t * p.num_mp) * 2 + (int)crank;
+      const int m0 = m_t * C::BM, n0 = n_t * BN + half * (BN / 2);
       const int row_base = m0 + q * 32;
+      const long long row0 = row_base + rs;
+      // operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs
+      float4 b4[NCH];
+      float bs[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        b4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bs[c] = 0.f;
+        if (p.bias) {
+          if (p.vec4) {
+            const int col = n0 + c * 32 + cg * 4;
+            if (col < p.N) b4[c] = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          } else {
+            const int col = n0 + c * 32 + lane;
+            if (col < p.N) bs[c] = __ldg(p.bias + col);
+          }
+        }
+      }
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       float run_max = -INFINITY, run_sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) +
+                          (uint32_t)(acc * BN + half * (BN / 2) + c * 32), r);
+        // issue this chunk's global operand loads while the TMEM load is in flight
+        const int col = col0 + cg * 4;
+        const bool colok = col < p.N;  // N % 4 == 0 in vec mode
+        bool ok[8];
+        float4 res[8];
+        uint2 dsrc[8];
+        if (p.vec4) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) ok[it] = colok && (row_base + it * 4 + rs) < p.M;
+          if (p.residual) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              res[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(p.residual + (row0 + it * 4) * p.ldr + col))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (p.dgelu_src) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              dsrc[it] = ok[it] ? __ldg(reinterpret_cast<const uint2*>(p.dgelu_src + (row0 + it * 4) * p.ldg + col))
+                                : make_uint2(0u, 0u);
+          }
+        }
         tmem_ld_wait();
+        if (c == NCH - 1 || col0 + 32 >= p.N) {
+          // last TMEM read of this accumulator: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
         if (p.lse_partial) {
           float cm = -INFINITY;
 #pragma unroll
@@ -231,32 +297,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           run_sum = run_sum * __expf(run_max - nm) + add;
           run_max = nm;
         }
-        {  // phase 1: thread = row, 8 x STS.128 (pitch 36 floats -> conflict-free quarter-warps)
-          float4* dst = reinterpret_cast<float4*>(epi + lane * C::EPI_PITCH);
+        {  // phase 1: thread = row; 8 x STS.128, 16-byte chunk j of row r stored at j ^ (r & 7)
+          float4* dst = reinterpret_cast<float4*>(epi + lane * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            dst[j ^ (lane & 7)] =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
         __syncwarp();
         if (p.vec4) {
-          // phase 2 (vector): lane -> (row sub-index rs, 4-column group cg); 8 iterations of
-          // 4 rows x 32 columns, every global access is a full 16 B (fp32) / 8 B (bf16) vector.
-          const int rs = lane >> 3, cg = lane & 7;
-          const int col = col0 + cg * 4;
-          const bool colok = col < p.N;  // N % 4 == 0 in vec mode
+          // phase 2 (vector): 8 iterations of 4 rows x 32 columns; every global access is a full
+          // 16-byte (fp32) / 8-byte (bf16) vector, 128 contiguous bytes per row.
           float v[8][4];
-          bool ok[8];
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && colok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + rs;
-            const float4 t = *reinterpret_cast<const float4*>(epi + rl * C::EPI_PITCH + cg * 4);
-            v[it][0] = t.x + b4.x; v[it][1] = t.y + b4.y; v[it][2] = t.z + b4.z; v[it][3] = t.w + b4.w;
-            ok[it] = colok && (row_base + rl) < p.M;
+            const float4 t = *reinterpret_cast<const float4*>(epi + rl * 32 + ((cg ^ (rl & 7)) << 2));
+            v[it][0] = t.x + b4[c].x; v[it][1] = t.y + b4[c].y;
+            v[it][2] = t.z + b4[c].z; v[it][3] = t.w + b4[c].w;
           }
-          const long long row0 = row_base + rs;
           if (p.out2) {
 #pragma unroll
             for (int it = 0; it < 8; ++it)
@@ -271,41 +331,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
             for (int it = 0; it < 8; ++it)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[it][e] = tanhf(v[it][e]);
+              for (int e = 0; e < 4; ++e) v[it][e] = tanh_fast(v[it][e]);
           } else if (p.act == MMTG_ACT_GELU_NEW) {
 #pragma unroll
             for (int it = 0; it < 8; ++it)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[it][e] = gelu_new_f(v[it][e]);
+              for (int e = 0; e < 4; ++e) v[it][e] = gelu_new_fast(v[it][e]);
           }
           if (p.dgelu_src) {
-            uint2 u[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              u[it] = ok[it] ? __ldg(reinterpret_cast<const uint2*>(p.dgelu_src + (row0 + it * 4) * p.ldg + col))
-                             : make_uint2(0u, 0u);
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u[it].x));
-              const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u[it].y));
+              const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].x));
+              const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].y));
               if (p.dact_tanh_out) {
                 v[it][0] *= 1.f - a.x * a.x; v[it][1] *= 1.f - a.y * a.y;
                 v[it][2] *= 1.f - b.x * b.x; v[it][3] *= 1.f - b.y * b.y;
               } else {
-                v[it][0] *= dgelu_new_f(a.x); v[it][1] *= dgelu_new_f(a.y);
-                v[it][2] *= dgelu_new_f(b.x); v[it][3] *= dgelu_new_f(b.y);
+                v[it][0] *= dgelu_new_fast(a.x); v[it][1] *= dgelu_new_fast(a.y);
+                v[it][2] *= dgelu_new_fast(b.x); v[it][3] *= dgelu_new_fast(b.y);
               }
             }
           }
           if (p.residual) {
-            float4 t[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              t[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(p.residual + (row0 + it * 4) * p.ldr + col))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              v[it][0] += t[it].x; v[it][1] += t[it].y; v[it][2] += t[it].z; v[it][3] += t[it].w;
+              v[it][0] += res[it].x; v[it][1] += res[it].y; v[it][2] += res[it].z; v[it][3] += res[it].w;
             }
           }
           if (p.rowtab0) {
@@ -371,42 +421,56 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
           }
         } else {
-          // phase 2 (scalar, unaligned pitches e.g. the contiguous [.., 13317] logits):
-          // lane = column, coalesced 4-byte accesses; supports bias / act / residual / colsum.
-          const int col = col0 + lane;
-          const bool colok = col < p.N;
-          const float bias_v = (p.bias && colok) ? __ldg(p.bias + col) : 0.f;
-          float csum = 0.f;
+          // phase 2 (scalar; unaligned pitches such as the contiguous [.., 13317] logits):
+          // lane = column -> every store instruction writes 128 contiguous bytes of one row.
+          // Supports bias / act / residual / colsum.
+          const int scol = col0 + lane;
+          const bool scolok = scol < p.N;
           const int nrows = min(32, p.M - row_base);  // warp-uniform, may be <= 0
-#pragma unroll 8
-          for (int rr = 0; rr < nrows; ++rr) {
-            const long long row = row_base + rr;
-            float v = epi[rr * C::EPI_PITCH + lane] + bias_v;
-            if (colok) {
-              if (p.act == MMTG_ACT_TANH) v = tanhf(v);
-              else if (p.act == MMTG_ACT_GELU_NEW) v = gelu_new_f(v);
-              if (p.residual) v += __ldg(p.residual + row * p.ldr + col);
-              csum += v;
-              if (p.atomic) atomicAdd((float*)p.out + row * p.ldo + col, v);
-              else if (p.out_bf16) ((bf16*)p.out)[row * p.ldo + col] = __float2bfloat16(v);
-              else ((float*)p.out)[row * p.ldo + col] = v;
+          const int sw = lane >> 2, sl = lane & 3;    // swizzled position of this lane's column
+          float csum = 0.f;
+          if (p.out_bf16 || p.atomic || p.residual || p.act != MMTG_ACT_NONE || p.colsum) {
+            for (int rr = 0; rr < nrows; ++rr) {
+              const long long row = row_base + rr;
+              float v = epi[rr * 32 + ((sw ^ (rr & 7)) << 2) + sl] + bs[c];
+              if (scolok) {
+                if (p.act == MMTG_ACT_TANH) v = tanh_fast(v);
+                else if (p.act == MMTG_ACT_GELU_NEW) v = gelu_new_fast(v);
+                if (p.residual) v += __ldg(p.residual + row * p.ldr + scol);
+                csum += v;
+                if (p.atomic) atomicAdd((float*)p.out + row * p.ldo + scol, v);
+                else if (p.out_bf16) ((bf16*)p.out)[row * p.ldo + scol] = __float2bfloat16(v);
+                else ((float*)p.out)[row * p.ldo + scol] = v;
+              }
+            }
+            if (p.colsum && scolok && nrows > 0) atomicAdd(p.colsum + scol, csum);
+          } else {
+            // lean path: fp32 store (+bias) only — the lm_head logits
+            float* orow = (float*)p.out + (long long)row_base * p.ldo + scol;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const float v = epi[rr * 32 + ((sw ^ (rr & 7)) << 2) + sl] + bs[c];
+              if (rr < nrows && scolok) orow[(long long)rr * p.ldo] = v;
             }
           }
-          if (p.colsum && colok && nrows > 0) atomicAdd(p.colsum + col, csum);
         }
         __syncwarp();
       }
       if (p.lse_partial) {
+        // the two column halves of a 128/256-wide tile keep separate partial slots
         const long long row = row_base + lane;
         if (row < p.M) {
-          float* dst = p.lse_partial + ((long long)n_t * p.M + row) * 2;
+          float* dst = p.lse_partial + ((long long)(n_t * 2 + half) * p.M + row) * 2;
           dst[0] = run_max;
           dst[1] = run_sum;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (n0 >= p.N) {
+        // this half-tile lies entirely beyond N: nothing was read, still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_ph ^= 1;
@@ -416,6 +480,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA until it is done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -513,9 +578,25 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int total = p.num_m * p.num_n * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  const int total = p.num_mp * p.num_n * p.splits;  // work units of a CTA pair
+  const int max_clusters = num_sms() / 2;
+  const int grid = 2 * (total < max_clusters ? total : max_clusters);
+  ProfScope prof(0, 2.0 * p.M * p.N * p.K,
+                 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + (p.out_bf16 ? 2.0 : 4.0) * p.M * p.N, st);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN>, tmA, tmB, p));
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;
@@ -534,6 +615,7 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
     // 256-wide tiles unless that leaves most of the machine idle
     const long long t256 = (long long)cdiv(a->M, 128) * cdiv(a->N, 256);
     BN = (a->N >= 256 && t256 >= 96) ? 256 : 128;
+    if (a->N <= 128) BN = 128;
   }
   MMTG_CHECK_ARG(BN == 128 || BN == 256, "block_n must be 0, 128 or 256");
   const bool atomic = a->accumulate != 0 || a->split_k > 1;
@@ -544,6 +626,7 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_m = cdiv(a->M, 128);
+  p.num_mp = (p.num_m + 1) / 2;
   p.num_n = cdiv(a->N, BN);
   p.num_kb = cdiv(a->K, 64);
   int splits = a->split_k > 1 ? a->split_k : 1;
@@ -579,7 +662,7 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   CUtensorMap tmA, tmB;
   if (!p.a_mn) MMTG_TRY(make_tmap_bf16_2d(&tmA, a->A, a->K, a->M, a->lda, 64, 128));
   else         MMTG_TRY(make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, 64, 64));
-  if (!p.b_mn) MMTG_TRY(make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, 64, BN));
+  if (!p.b_mn) MMTG_TRY(make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, 64, BN / 2));
   else         MMTG_TRY(make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, 64));
 
   cudaStream_t st = (cudaStream_t)stream;

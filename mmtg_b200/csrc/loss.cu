@@ -85,7 +85,7 @@ ce_reduce_kernel(const float* __restrict__ logits, long long ld, const float* __
   const int b = blockIdx.x;
   float a_hf = 0.f, a_ce = 0.f;
   for (int t = threadIdx.x; t < L - 1; t += 256) {
-    if (t + 1 < P && topic_ids == nullptr) continue;
+    if (t + 1 < P && topic_ids == nullptr) continue;  // generic MyLoss path: prompt labels unknown
     const int lab = label_at(topic_ids, targets, b, t + 1, P, T);
     const long long row = (long long)b * L + t;
     const float nll = lse[row] - __ldg(logits + row * ld + lab);
@@ -106,7 +106,7 @@ ce_reduce_kernel(const float* __restrict__ logits, long long ld, const float* __
       a_ce += s2[w];
     }
     if (hf_sum) hf_sum[b] = a_hf;
-    if (ce) ce[b] = a_ce / (float)(L - 1 - P);
+    if (ce) ce[b] = (L - 1 - P) > 0 ? a_ce / (float)(L - 1 - P) : 0.f;
   }
 }
 
@@ -187,6 +187,7 @@ ce_bwd_kernel(const float* __restrict__ logits, long long ld, const float* __res
 }  // namespace
 
 int lse_rows(const float* logits, long long ld, float* lse, int M, int V, cudaStream_t st) {
+  ProfScope prof(2, 0, (double)M * V * 4, st);
   lse_rows_kernel<<<M, 256, 0, st>>>(logits, ld, lse, V);
   MMTG_LAUNCH_OK();
   count_launch();
@@ -227,6 +228,7 @@ int negloss(const float* ce, const int* ratings, int stage, float* loss, float* 
 int ce_bwd(const float* logits, long long ld, const float* lse, const int* topic_ids,
            const int* targets, const float* coef, const float* g_my, const float* g_hf, void* out,
            int out_bf16, long long ldo, int B, int L, int P, int T, int V, cudaStream_t st) {
+  ProfScope prof(2, 0, (double)B * L * ((double)V * 4 + (double)ldo * (out_bf16 ? 2 : 4)), st);
   if (out_bf16)
     ce_bwd_kernel<true><<<B * L, 256, 0, st>>>(logits, ld, lse, topic_ids, targets, coef, g_my, g_hf, out, ldo, B, L, P, T, V);
   else

@@ -113,6 +113,7 @@ extern "C" int mmtg_adamw_step(float* params, const float* grads, float* exp_avg
     step_size = (float)((double)lr * sqrt(bc2) / bc1);
   }
   const int blocks = num_sms() * 8;
+  ProfScope prof(2, 0, (double)n * 30.0, (cudaStream_t)stream);
   adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq,
                                                           (bf16*)params_bf16, n, lr, beta1, beta2, eps,
                                                           weight_decay, step_size, normsq, max_norm);

@@ -1,0 +1,165 @@
+"""Drop-in generation surface (mirrors /root/reference/src/generate.py:64-145).
+
+`sample_sequence(model, start_input, length, tokenizer, temperature, top_k, top_p,
+repitition_penalty, device)` keeps the reference's signature (sic: `repitition`) and return value
+(the token list WITHOUT the last appended token). Underneath, the reference's "re-run the whole
+model on the whole prefix per token" loop is replaced by a KV-cached decode engine:
+one training-style forward over [prompt | first token], then one fused step per position
+(mmtg_decode_step + mmtg_sample_rows, both hand-written CUDA; the step index lives on the
+device so the step is replayed from a CUDA graph). `sample_sequence_batch` runs B independent
+batch-1 reference runs at once (BASELINE.json configs[3]: batch 64).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_FLOAT_KEYS = ("topic_emb", "img_embs", "r_embs")
+_INT_KEYS = ("topic_ids", "tpw_attention_mask", "tpw_type_ids")
+
+
+def top_k_top_p_filtering(logits, top_k=0, top_p=0.0, filter_value=-float("Inf")):
+    """src/generate.py:64-94 on the device sampler: returns `logits` with every token the
+    reference would filter set to `filter_value` (1-D logits; temperature 1, no penalty)."""
+    assert logits.dim() == 1
+    if not logits.is_cuda:
+        raise _lib.MMTGError("mmtg_b200.top_k_top_p_filtering runs on CUDA only")
+    V = logits.numel()
+    kept, _ = _filtered_distribution(logits.detach().float().view(1, V), top_k, top_p, ban=False)
+    keep = torch.zeros(V, dtype=torch.bool, device=logits.device)
+    keep[kept[0][kept[0] >= 0].long()] = True
+    logits[~keep] = filter_value
+    return logits
+
+
+def _filtered_distribution(logits2d, top_k, top_p, temperature=1.0, ban=True):
+    """(kept ids [B, 1024] (-1 padded), probabilities [B, 1024]) of the sampler's distribution."""
+    Bn, V = logits2d.shape
+    dev = logits2d.device
+    z = logits2d.contiguous()
+    gen = torch.full((Bn, 4), 5, dtype=torch.int32, device=dev)  # dummy history, never PAD
+    j = torch.zeros(1, dtype=torch.int32, device=dev)
+    dbg = torch.empty(Bn, 1024, 2, device=dev)
+    _lib.check(_lib.lib().mmtg_sample_rows(C.c_void_p(z.data_ptr()), C.c_int64(z.stride(0)), C.c_void_p(gen.data_ptr()),
+                                           4, C.c_void_p(j.data_ptr()), Bn, V, 1 << 20, C.c_float(temperature),
+                                           int(top_k), C.c_float(top_p), C.c_float(1.0), C.c_uint64(0), int(ban),
+                                           C.c_void_p(dbg.data_ptr()), C.c_void_p(_lib.stream_ptr())),
+               "mmtg_sample_rows")
+    return dbg[..., 0], dbg[..., 1]
+
+
+def _collate(start_inputs):
+    if isinstance(start_inputs, dict):
+        return {k: np.asarray(v) for k, v in start_inputs.items()}
+    return {k: np.stack([np.asarray(s[k]) for s in start_inputs]) for k in start_inputs[0] if k != "rating"}
+
+
+def returned_length(length, sent_len):
+    """Length of the list the reference returns: `generated` is captured at the last iteration
+    that runs the model (src/generate.py:126,144), i.e. targets[: i_last + 1]."""
+    i_last = -1
+    for i in range(length):
+        if i > 0 and (i + 2) % sent_len in (0, 1):
+            continue
+        i_last = i
+    return i_last + 1
+
+
+@torch.no_grad()
+def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperature=1.0, top_k=30, top_p=0.0,
+                          repitition_penalty=1.0, device="cuda", seed=0, use_cuda_graph=True,
+                          return_step_logits=False):
+    """B independent runs of the reference's sample_sequence. `start_inputs`: list of per-sample
+    dicts (MyDataset items with 'targets' = [start id]) or one dict of batched arrays.
+    Returns a list of B token-id lists."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.MMTGError("mmtg_b200 generation runs on CUDA only (no CPU fallback)")
+    lib = _lib.lib()
+    host = _collate(start_inputs)
+    Bn = host["topic_ids"].shape[0]
+    batch = {k: torch.as_tensor(host[k], dtype=torch.float32).to(dev) for k in _FLOAT_KEYS}
+    for k in _INT_KEYS:
+        batch[k] = torch.as_tensor(host[k]).long().to(dev)
+    first = torch.as_tensor(host["targets"]).long().view(Bn, -1)[:, :1].to(dev)
+    batch["targets"] = first
+    batch["attention_mask"] = torch.ones_like(first)
+    batch["type_ids"] = torch.zeros_like(first)
+    dc = model.data_config
+    sent_len = dc["max_sent_length"] + 2
+    n_sent = dc["max_seq_length"] // sent_len
+    # ---- prefill: [prompt | first token] through the training-style engine (inference branch) ----
+    prev_flag = model.train_flag
+    model.train_flag = False
+    try:
+        _, _, logits0 = model(batch)
+    finally:
+        model.train_flag = prev_flag
+    step = logits0._mmtg_step
+    d = step.dims
+    Lmax = d.P + length + 1
+    st = C.c_void_p(_lib.stream_ptr())
+    nbytes = lib.mmtg_decode_workspace_bytes(C.byref(d), Lmax)
+    dws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.mmtg_decode_load_prefix(C.byref(d), C.c_void_p(step.ws.data_ptr()), Lmax, C.c_void_p(dws.data_ptr()),
+                                           C.c_void_p(step.mask.data_ptr()), st), "mmtg_decode_load_prefix")
+    gen_ld = length + 1
+    gen = torch.zeros(Bn, gen_ld, dtype=torch.int32, device=dev)
+    gen[:, 0] = first[:, 0].to(torch.int32)
+    j = torch.zeros(1, dtype=torch.int32, device=dev)
+    step_logits = torch.empty(Bn, d.V, device=dev)
+    cm = model._c_model(d, dev)
+    kept = []
+
+    def sample(ptr, ld):
+        _lib.check(lib.mmtg_sample_rows(C.c_void_p(ptr), C.c_int64(ld), C.c_void_p(gen.data_ptr()), gen_ld,
+                                        C.c_void_p(j.data_ptr()), Bn, d.V, sent_len, C.c_float(temperature),
+                                        int(top_k), C.c_float(top_p), C.c_float(repitition_penalty),
+                                        C.c_uint64(seed), 1, None, C.c_void_p(_lib.stream_ptr())), "mmtg_sample_rows")
+
+    def one_step():
+        _lib.check(lib.mmtg_decode_step(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), C.c_void_p(gen.data_ptr()),
+                                        gen_ld, C.c_void_p(j.data_ptr()), sent_len, n_sent,
+                                        C.c_void_p(step_logits.data_ptr()), C.c_void_p(_lib.stream_ptr())),
+                   "mmtg_decode_step")
+        sample(step_logits.data_ptr(), d.V)
+
+    # reference iteration i = 0: logits of the last prefix row decide targets[1]
+    if return_step_logits:
+        kept.append(logits0[:, -1, :].clone())
+    sample(logits0.data_ptr() + 4 * (d.L - 1) * d.V, d.L * d.V)
+    remaining = length - 1
+    eager = min(remaining, 2 if (use_cuda_graph and not return_step_logits) else remaining)
+    for _ in range(eager):
+        one_step()
+        if return_step_logits:
+            kept.append(step_logits.clone())
+    remaining -= eager
+    if remaining > 0:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                one_step()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(remaining):
+            graph.replay()
+    out = gen.cpu().numpy()
+    n_ret = returned_length(length, sent_len)
+    rows = [out[b, :n_ret].tolist() for b in range(Bn)]
+    if return_step_logits:
+        return rows, kept
+    return rows
+
+
+def sample_sequence(model, start_input, length, tokenizer=None, temperature=1.0, top_k=30, top_p=0.0,
+                    repitition_penalty=1.0, device="cuda", seed=0):
+    """Reference signature (src/generate.py:97-107): one sample in, list of token ids out."""
+    one = {k: np.asarray(v)[None] for k, v in start_input.items() if k != "rating"}
+    return sample_sequence_batch(model, one, length, tokenizer, temperature, top_k, top_p, repitition_penalty,
+                                 device, seed)[0]

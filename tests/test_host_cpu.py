@@ -1,0 +1,134 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/mmtg_b200.h declares
+(no compute without a GPU), the drop-in module reproduces the reference's state_dict layout, and
+host-side logic (inference-branch type ids / masks, returned-length rule, synthetic batch layout)
+matches the oracle / reference rules."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mmtg_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mmtg_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(mmtg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    lib = _lib.lib()
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert lib.mmtg_abi_version() == 1
+    lib.mmtg_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.mmtg_last_error(), bytes)
+
+
+def test_ctypes_structs_match_header_sizes():
+    from mmtg_b200 import _lib
+    from mmtg_b200.model import Batch, Dims, LayerOffsets, Model, ParamOffsets
+    assert ctypes.sizeof(Dims) == 16 * 4
+    assert ctypes.sizeof(LayerOffsets) == 12 * 8
+    assert ctypes.sizeof(ParamOffsets) == (2 + 8 + 6 + 4 + 4 + 4 + 4) * 8 + 48 * 12 * 8
+    assert ctypes.sizeof(Batch) == 7 * 8
+    assert ctypes.sizeof(Model) == ctypes.sizeof(Dims) + ctypes.sizeof(ParamOffsets) + 4 * 8
+    assert ctypes.sizeof(_lib.GemmArgs) % 8 == 0
+
+
+def test_workspace_size_query_runs_without_gpu():
+    from mmtg_b200 import _lib
+    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200.model import MMTG
+    m = MMTG(model_cfgs, data_config(), 13317)
+    d = m._dims(32, 221)
+    n = _lib.lib().mmtg_train_workspace_bytes(ctypes.byref(d))
+    assert 2e9 < n < 8e9, n
+    d.E = 700  # head_dim != 64 -> rejected with a message, not a crash
+    assert _lib.lib().mmtg_train_workspace_bytes(ctypes.byref(d)) == -1
+    assert b"head_dim" in _lib.lib().mmtg_last_error()
+
+
+def test_state_dict_layout_and_flat_layout():
+    from mmtg_b200 import synth
+    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200.model import MMTG
+    m = MMTG(model_cfgs, data_config(), 13317)
+    sd = m.state_dict()
+    assert list(sd.keys()) == synth.state_dict_keys() and len(sd) == 193
+    assert sum(p.numel() for p in m.parameters()) == 109_064_709
+    assert sd["decoder.gpt2.lm_head.weight"].data_ptr() == sd["decoder.gpt2.transformer.wte.weight"].data_ptr()
+    ref = synth.make_state_dict(0)
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    # q|k|v stacked contiguously; every tensor 64-element aligned; blocks form contiguous buckets
+    lay = m._layout
+    for pre in ("img", "text"):
+        q, k, v = (lay[f"{pre}_inner_atten_layer.{n}.weight"] for n in ("query", "key", "value"))
+        assert k[0] == q[0] + q[1] and v[0] == k[0] + k[1]
+    spans = sorted(lay.values())
+    for (o1, n1), (o2, _) in zip(spans, spans[1:]):
+        assert o1 + n1 <= o2
+    lo, hi = m.layer_bucket(3)
+    assert hi - lo >= 7_087_872 and m.layer_bucket(4)[0] >= hi
+    assert m.tail_bucket()[1] == m._flat_numel
+    # no CPU path: forward on CPU tensors fails loudly
+    batch = synth.batch_to_torch(synth.make_batch(1))
+    with pytest.raises(Exception):
+        m(batch)
+
+
+def test_inference_types_and_mask_match_oracle():
+    from mmtg_b200.configs import data_config
+    from mmtg_b200.model import _inference_types_and_mask
+    from oracle import mmtg_oracle as O
+    dc = data_config()
+    rng = np.random.default_rng(0)
+    for T in (1, 5, 22, 23, 45, 130, 221):
+        ids = torch.from_numpy(rng.integers(0, 300, (2, T)))
+        ids[0, rng.integers(0, T)] = 0
+        tt = torch.from_numpy(rng.integers(0, 2, (2, 15)))
+        tm = torch.from_numpy(rng.integers(0, 2, (2, 15)))
+        a = _inference_types_and_mask(ids, tt, tm, dc)
+        b = O.inference_type_ids_and_mask(ids[0], tt, tm, 22, 220)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), T
+
+
+def test_returned_length_rule():
+    from mmtg_b200.generate import returned_length
+    assert returned_length(220, 22) == 218   # reference: i = 218, 219 are forced slots
+    assert returned_length(50, 22) == 50     # [probed] in SURVEY §3.4: length=50 -> 50 ids
+    assert returned_length(48, 22) == 48
+    assert returned_length(21, 22) == 20
+    assert returned_length(1, 22) == 1
+
+
+def test_synthetic_batch_follows_dataset_layout():
+    from mmtg_b200 import synth
+    b = synth.make_batch(4, seed=3)
+    assert b["targets"].shape == (4, 221) and b["topic_ids"].shape == (4, 15)
+    t, m, ty = b["targets"], b["attention_mask"], b["type_ids"]
+    assert (t[:, 220] == 102).all() and (m[:, 220] == 1).all()
+    for s in range(10):
+        assert (t[:, 22 * s] == 1).all() and (t[:, 22 * s + 21] == 2).all()
+        body = slice(22 * s + 1, 22 * s + 21)
+        assert ((t[:, body] == 0) == (m[:, body] == 0)).all()
+        want = 1 if s // 2 == 4 else s // 2 + 1
+        assert set(np.unique(ty[:, body])) <= {0, want}
+    assert (ty[:, ::22][:, :10] == 0).all()
+    assert np.allclose(np.linalg.norm(b["img_embs"], axis=-1), 1.0, atol=1e-5)
+    assert b["rating"].min() >= 1 and b["rating"].max() <= 5
+
+
+def test_fused_adamw_matches_hf_adamw_formula_on_paper():
+    """The update rule restated in optim.cu (HF AdamW: eps outside the bias-corrected denominator)."""
+    lr, b1, b2, eps = 1e-3, 0.9, 0.999, 1e-6
+    p, g, m, v = 0.5, 0.2, 0.0, 0.0
+    for t in (1, 2, 3):
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        step = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        p -= step * m / (v ** 0.5 + eps)
+    assert abs(p - (0.5 - 3 * lr)) < 1e-5  # constant gradient -> |update| ~ lr per step

@@ -1,0 +1,52 @@
+"""world_size-2 gloo test (CPU) of the bucketed gradient exchange: stage -> bucket mapping covers
+the flat gradient buffer exactly once and the all-reduce averages across ranks."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _FakeModel:
+    """Flat gradient buffer with the same bucket API as mmtg_b200.model.MMTG."""
+
+    def __init__(self, nl, per_layer, tail, rank):
+        self.nl, self.per, self.tail = nl, per_layer, tail
+        n = nl * per_layer + tail
+        self._flat = (None, None, torch.full((n,), float(rank + 1)))
+
+    def layer_bucket(self, l):
+        return l * self.per, (l + 1) * self.per
+
+    def tail_bucket(self):
+        return self.nl * self.per, self.nl * self.per + self.tail
+
+
+def _worker(rank, world, port):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmtg_b200.parallel import GradSync
+    m = _FakeModel(nl=4, per_layer=1000, tail=333, rank=rank)
+    sync = GradSync()
+    nstage = m.nl + 2
+    touched = torch.zeros_like(m._flat[2])
+    for s in range(nstage):
+        before = m._flat[2].clone()
+        sync.after_stage(m, s, nstage)
+        touched += (m._flat[2] != before).float()
+    sync.finish(m)
+    expect = sum(r + 1 for r in range(world)) / world
+    assert torch.allclose(m._flat[2], torch.full_like(m._flat[2], expect))
+    assert (touched == 1).all(), "every element must be reduced exactly once"
+    assert sync.bytes_reduced == m._flat[2].numel() * 4
+    dist.destroy_process_group()
+
+
+def test_gradsync_gloo_world2():
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
