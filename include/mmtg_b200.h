@@ -103,10 +103,13 @@ int mmtg_gemm_bf16(const mmtg_gemm_args* args, void* stream);
 int mmtg_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
                        float* y_f32, float* mean, float* rstd, int32_t M, int32_t E, float eps,
                        void* stream);
-/* its autograd backward; dx written or accumulated; dgamma/dbeta accumulated (atomics) */
+/* its autograd backward; dx written or accumulated; dgamma/dbeta accumulated (atomics).
+ * Optional fusions for the residual stream: dx_bf16 = bf16 copy of the final dx (next GEMM
+ * operand), dx_colsum[E] += column sums of the final dx (bias gradient of the layer below). */
 int mmtg_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const float* x, const float* mean,
                        const float* rstd, const float* gamma, float* dx, int32_t accumulate_dx,
-                       float* dgamma, float* dbeta, int32_t M, int32_t E, void* stream);
+                       float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, int32_t M,
+                       int32_t E, void* stream);
 int mmtg_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* bias gradients: out[N] += column sums of x[M,N]; optional bf16 copy of an fp32 x */
 int mmtg_colsum(const void* x, int32_t x_is_bf16, int64_t ld, void* copy_bf16, int64_t ldc,

@@ -262,21 +262,29 @@ attn_fwd_kernel(const AttnParams p) {
 // --------------------------------------------------------------------------------------------
 // backward preprocess: delta[b,h,q] = sum_d dO[q,d] * O[q,d]
 // --------------------------------------------------------------------------------------------
-__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
-                                  float* __restrict__ delta, int B, int L, int NH, int E) {
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One warp per row: lane i-th 8-byte load covers elements [i*128 + lane*4, +4) -> head 2i + (lane>=16).
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                  float* __restrict__ delta, int B, int L, int NH, int E) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= (long long)B * L) return;
   const int l = lane_id();
-  const long long total = (long long)B * L * NH;
-  if (gw >= total) return;
-  const int h = (int)(gw % NH);
-  const long long row = gw / NH;  // b*L + q
-  const long long off = row * E + h * HD + l * 2;
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + off));
-  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
-  const float s = warp_sum(a.x * d.x + a.y * d.y);
-  if (l == 0) {
-    const int b = (int)(row / L), q = (int)(row - (long long)b * L);
-    delta[((long long)b * NH + h) * L + q] = s;
+  const int b = (int)(row / L), q = (int)(row - (long long)b * L);
+  const uint2* o = reinterpret_cast<const uint2*>(out + row * E);
+  const uint2* d = reinterpret_cast<const uint2*>(dout + row * E);
+  for (int i = 0; i * 128 < E; ++i) {
+    const uint2 a = __ldg(o + i * 32 + l), g = __ldg(d + i * 32 + l);
+    const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.x));
+    const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.y));
+    const float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.x));
+    const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.y));
+    float s = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((l & 15) == 0) {
+      const int h = 2 * i + (l >> 4);
+      delta[((long long)b * NH + h) * L + q] = s;
+    }
   }
 }
 
@@ -522,7 +530,7 @@ int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dou
   p.qkv = qkv; p.kmask = kmask; p.lse = const_cast<float*>(lse); p.dout = dout; p.delta = delta;
   p.dqkv = dqkv; p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
   ProfScope prof(1, 2.5 * 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 8 * B * L * NH * 64, st);
-  const long long warps = (long long)B * L * NH;
+  const long long warps = (long long)B * L;
   attn_delta_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, st>>>(out, dout, delta, B, L, NH, p.E);
   MMTG_LAUNCH_OK();
   dim3 grid(cdiv(L, BQ), B * NH);

@@ -78,19 +78,20 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, float* __restrict__ dx, int accumulate_dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ dx16,
+              float* __restrict__ dx_colsum, int M) {
   constexpr int V = E / 128;
-  __shared__ float s_dg[E], s_db[E];
-  for (int i = threadIdx.x; i < E; i += blockDim.x) s_dg[i] = s_db[i] = 0.f;
+  __shared__ float s_dg[E], s_db[E], s_cs[E];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) s_dg[i] = s_db[i] = s_cs[i] = 0.f;
   __syncthreads();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int l = lane_id();
-  float4 gam[V], adg[V], adb[V];
+  float4 gam[V], adg[V], adb[V], acs[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + l + i * 32);
-    adg[i] = adb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    adg[i] = adb[i] = acs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = warp; row < M; row += nwarps) {
     const float mu = mean[row], rs = rstd[row];
@@ -132,6 +133,20 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
         o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
       }
       *dst = o;
+      if (dx16) {  // bf16 copy of the (accumulated) residual-stream gradient: next GEMM operand
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        reinterpret_cast<uint2*>(dx16 + (long long)row * E)[c4] =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+      acs[i].x += o.x; acs[i].y += o.y; acs[i].z += o.z; acs[i].w += o.w;
+    }
+  }
+  if (dx_colsum) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = (l + i * 32) * 4;
+      atomicAdd(&s_cs[c], acs[i].x); atomicAdd(&s_cs[c + 1], acs[i].y);
+      atomicAdd(&s_cs[c + 2], acs[i].z); atomicAdd(&s_cs[c + 3], acs[i].w);
     }
   }
 #pragma unroll
@@ -146,6 +161,7 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
     if (dgamma) atomicAdd(dgamma + i, s_dg[i]);
     if (dbeta) atomicAdd(dbeta + i, s_db[i]);
+    if (dx_colsum) atomicAdd(dx_colsum + i, s_cs[i]);
   }
 }
 
@@ -338,11 +354,11 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y
 
 int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd,
                   const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
-                  int M, int E, cudaStream_t st) {
+                  bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st) {
   MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
   const int blocks = min(cdiv(M, 8), num_sms() * 2);
-  ProfScope prof(2, 0, (double)M * E * (4 + (dy_bf16 ? 2 : 4) + 4 + (accumulate_dx ? 4 : 0)), st);
-#define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, M)
+  ProfScope prof(2, 0, (double)M * E * (4 + (dy_bf16 ? 2 : 4) + 4 + (accumulate_dx ? 4 : 0) + (dx16 ? 2 : 0)), st);
+#define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, dx16, dx_colsum, M)
   if (E == 768) { if (dy_bf16) LNB(768, true); else LNB(768, false); }
   else { if (dy_bf16) LNB(512, true); else LNB(512, false); }
 #undef LNB
@@ -427,11 +443,11 @@ extern "C" int mmtg_layernorm_fwd(const float* x, const float* gamma, const floa
 }
 extern "C" int mmtg_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const float* x, const float* mean,
                                   const float* rstd, const float* gamma, float* dx,
-                                  int32_t accumulate_dx, float* dgamma, float* dbeta, int32_t M,
-                                  int32_t E, void* stream) {
+                                  int32_t accumulate_dx, float* dgamma, float* dbeta, void* dx_bf16,
+                                  float* dx_colsum, int32_t M, int32_t E, void* stream) {
   MMTG_CHECK_ARG(dy && x && mean && rstd && gamma && dx && M > 0, "bad layernorm bwd args");
-  return layernorm_bwd(dy, dy_is_bf16, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, M, E,
-                       (cudaStream_t)stream);
+  return layernorm_bwd(dy, dy_is_bf16, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta,
+                       (bf16*)dx_bf16, dx_colsum, M, E, (cudaStream_t)stream);
 }
 extern "C" int mmtg_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   MMTG_CHECK_ARG(src && dst && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "cast needs 16-byte aligned buffers");

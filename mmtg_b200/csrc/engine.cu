@@ -391,36 +391,36 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       MMTG_TRY(Gemm(w.dlogits16, d.Vp, false, W + o.wte, E, true, M, E, d.V).out_bf16(w.dx, E).run(st));
       // dwte += dlogits^T · xf
       MMTG_TRY(wgrad(w.dlogits16, d.Vp, w.xf, E, G + o.wte, E, d.V, E, M, st));
+      // also emits g16 = bf16(dh) and the mlp c_proj bias gradient of the top block
       MMTG_TRY(layernorm_bwd(w.dx, 1, w.layer[d.NL - 1].h_out, w.meanf, w.rstdf, P + o.lnf_w, w.dh, 0,
-                             G + o.lnf_w, G + o.lnf_b, M, E, st));
+                             G + o.lnf_w, G + o.lnf_b, w.g16, G + o.layer[d.NL - 1].proj2_b, M, E, st));
     } else if (stage <= d.NL) {
       const int l = d.NL - stage;
       const LayerWs& L = w.layer[l];
       const mmtg_layer_offsets& lo = o.layer[l];
-      // ---- MLP ----
-      MMTG_TRY(colsum(w.dh, 0, E, w.g16, E, G + lo.proj2_b, M, E, st));
+      // ---- MLP ---- (g16 = bf16(dh) and d(proj2_b) were produced by the LayerNorm backward above)
       MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj2_w, E, false, M, 4 * E, E)
                    .out_bf16(w.du, 4 * E).dgelu(L.u, 4 * E).colsum(G + lo.fc_b).run(st));
       MMTG_TRY(wgrad(L.a, 4 * E, w.g16, E, G + lo.proj2_w, E, 4 * E, E, M, st));
       MMTG_TRY(Gemm(w.du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(w.dx, E).run(st));
       MMTG_TRY(wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, st));
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_mid, L.mean2, L.rstd2, P + lo.ln2_w, w.dh, 1, G + lo.ln2_w,
-                             G + lo.ln2_b, M, E, st));
+                             G + lo.ln2_b, w.g16, G + lo.proj_b, M, E, st));
       // ---- attention ----
-      MMTG_TRY(colsum(w.dh, 0, E, w.g16, E, G + lo.proj_b, M, E, st));
       MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(w.datt, E).run(st));
       MMTG_TRY(wgrad(L.att, E, w.g16, E, G + lo.proj_w, E, E, E, M, st));
       MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, w.datt, L.lse, w.delta, w.dqkv, B, d.L, d.NH, st));
       MMTG_TRY(colsum(w.dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, st));
       MMTG_TRY(Gemm(w.dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(w.dx, E).run(st));
       MMTG_TRY(wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, st));
+      // dh is now the gradient of this block's input: its bf16 copy / column sums feed the block
+      // below (mlp c_proj bias) or, for block 0, the projector (projector_layer2 bias)
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_in, L.mean1, L.rstd1, P + lo.ln1_w, w.dh, 1, G + lo.ln1_w,
-                             G + lo.ln1_b, M, E, st));
+                             G + lo.ln1_b, w.g16, l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, st));
     } else {
       // ---------------- embeddings + projector ----------------
       MMTG_TRY(posadd_bwd(w.dh, G + o.wpe, B, d.L, E, st));
       MMTG_TRY(typeadd_bwd(w.dh, b->type_ids, G + o.wte, M, E, st));
-      MMTG_TRY(colsum(w.dh, 0, E, w.g16, E, G + o.proj2_b, M, E, st));
       // dp1 = (g · W2) ⊙ (1 - p1²); W2 [E,He] as MN-major [N=He, K=E]
       MMTG_TRY(Gemm(w.g16, E, false, W + o.proj2_w, He, true, M, He, E)
                    .out_bf16(w.dp1, He).dtanh(w.p1, He).colsum(G + o.proj1_b).run(st));
@@ -436,7 +436,7 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
                         w.dactx[0], w.dactx[1], G + o.beta_att_w, G + o.beta_att_b, B, S, He, st));
       // ---------------- topic branch ----------------
       MMTG_TRY(layernorm_bwd(w.dtopic_ln, 0, w.topic_pre, w.topic_mean, w.topic_rstd, P + o.enc_ln_w[0],
-                             w.dtopic_pre, 0, G + o.enc_ln_w[0], G + o.enc_ln_b[0], B, He, st));
+                             w.dtopic_pre, 0, G + o.enc_ln_w[0], G + o.enc_ln_b[0], nullptr, nullptr, B, He, st));
       MMTG_TRY(colsum(w.dtopic_pre, 0, He, w.dtopic_pre16, He, G + o.topic_b, B, He, st));
       MMTG_TRY(wgrad(w.dtopic_pre16, He, w.x_topic16, Dw, G + o.topic_w, Dw, He, Dw, B, st));
       // ---------------- image / text branches: alpha attention, LayerNorm, GRU ----------------
@@ -449,7 +449,7 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
                      .out_f32(w.dln, He).run(st));
         MMTG_TRY(wgrad(w.daqkv16, 3 * He, w.ln16[md], He, G + o.alpha_qkv_w[md], He, 3 * He, He, SB, st));
         MMTG_TRY(layernorm_bwd(w.dln, 0, w.hout[md], w.ln_mean[md], w.ln_rstd[md], P + o.enc_ln_w[1 + md],
-                               w.dhout, 0, G + o.enc_ln_w[1 + md], G + o.enc_ln_b[1 + md], SB, He, st));
+                               w.dhout, 0, G + o.enc_ln_w[1 + md], G + o.enc_ln_b[1 + md], nullptr, nullptr, SB, He, st));
         // GRU backward through time
         for (int t = S - 1; t >= 0; --t) {
           const float* hp = t > 0 ? w.hout[md] + (size_t)(t - 1) * B * He : nullptr;

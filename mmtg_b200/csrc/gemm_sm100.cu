@@ -74,7 +74,13 @@ struct GemmCfg {
   static constexpr int THREADS = 320;
 };
 
-template <int BN>
+// epilogue feature bits (compile-time mask EPI)
+enum : uint32_t {
+  F_OUT2 = 1, F_ACT = 2, F_DACT = 4, F_RES = 8, F_ROWTAB = 16, F_COLSUM = 32, F_ATOMIC = 64,
+  F_LSE = 128, F_SCALAR = 256
+};
+
+template <int BN, uint32_t EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -215,6 +221,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ===================== epilogue warps (2..9) =====================
     // Two warps per TMEM lane quadrant: warps 2..5 own the left half of the tile's columns,
     // warps 6..9 the right half (a warp may only touch lanes 32*(warp%4) .. +31).
+    // EPI is a compile-time feature mask: disabled features generate no code, which keeps the
+    // per-chunk instruction footprint inside the instruction cache (the all-features epilogue
+    // was measured fetch-bound: stall_no_inst 47 %).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int NCH = BN / 64;  // 32-column chunks per warp
@@ -228,27 +237,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int m0 = m_t * C::BM, n0 = n_t * BN + half * (BN / 2);
       const int row_base = m0 + q * 32;
       const long long row0 = row_base + rs;
-      // operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs
-      float4 b4[NCH];
-      float bs[NCH];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        b4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bs[c] = 0.f;
+      // bias of the first chunk is fetched BEFORE waiting for the MMAs; later chunks prefetch
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float bs = 0.f;
+      auto load_bias = [&](int c, float4& o4, float& o1) {
+        o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        o1 = 0.f;
         if (p.bias) {
-          if (p.vec4) {
+          if constexpr (!(EPI & F_SCALAR)) {
             const int col = n0 + c * 32 + cg * 4;
-            if (col < p.N) b4[c] = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            if (col < p.N) o4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           } else {
             const int col = n0 + c * 32 + lane;
-            if (col < p.N) bs[c] = __ldg(p.bias + col);
+            if (col < p.N) o1 = __ldg(p.bias + col);
           }
         }
-      }
+      };
+      load_bias(0, b4, bs);
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       float run_max = -INFINITY, run_sum = 0.f;
-#pragma unroll
+      bool released = false;
+#pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
@@ -261,20 +271,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         bool ok[8];
         float4 res[8];
         uint2 dsrc[8];
-        if (p.vec4) {
+        float4 b4n;
+        float bsn;
+        load_bias(c + 1 < NCH ? c + 1 : c, b4n, bsn);
+        if constexpr (!(EPI & F_SCALAR)) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) ok[it] = colok && (row_base + it * 4 + rs) < p.M;
-          if (p.residual) {
+          if constexpr (EPI & F_RES) {
+            if (p.residual) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              res[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(p.residual + (row0 + it * 4) * p.ldr + col))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int it = 0; it < 8; ++it)
+                res[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(p.residual + (row0 + it * 4) * p.ldr + col))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
-          if (p.dgelu_src) {
+          if constexpr (EPI & F_DACT) {
+            if (p.dgelu_src) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              dsrc[it] = ok[it] ? __ldg(reinterpret_cast<const uint2*>(p.dgelu_src + (row0 + it * 4) * p.ldg + col))
-                                : make_uint2(0u, 0u);
+              for (int it = 0; it < 8; ++it)
+                dsrc[it] = ok[it] ? __ldg(reinterpret_cast<const uint2*>(p.dgelu_src + (row0 + it * 4) * p.ldg + col))
+                                  : make_uint2(0u, 0u);
+            }
           }
         }
         tmem_ld_wait();
@@ -283,19 +300,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
+          released = true;
         }
-        if (p.lse_partial) {
-          float cm = -INFINITY;
+        if constexpr (EPI & F_LSE) {
+          if (p.lse_partial) {
+            float cm = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) cm = fmaxf(cm, __uint_as_float(r[j]));
-          const float nm = fmaxf(run_max, cm);
-          float add = 0.f;
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) cm = fmaxf(cm, __uint_as_float(r[j]));
+            const float nm = fmaxf(run_max, cm);
+            float add = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) add += __expf(__uint_as_float(r[j]) - nm);
-          run_sum = run_sum * __expf(run_max - nm) + add;
-          run_max = nm;
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) add += __expf(__uint_as_float(r[j]) - nm);
+            run_sum = run_sum * __expf(run_max - nm) + add;
+            run_max = nm;
+          }
         }
         {  // phase 1: thread = row; 8 x STS.128, 16-byte chunk j of row r stored at j ^ (r & 7)
           float4* dst = reinterpret_cast<float4*>(epi + lane * 32);
@@ -306,7 +326,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
         __syncwarp();
-        if (p.vec4) {
+        if constexpr (!(EPI & F_SCALAR)) {
           // phase 2 (vector): 8 iterations of 4 rows x 32 columns; every global access is a full
           // 16-byte (fp32) / 8-byte (bf16) vector, 128 contiguous bytes per row.
           float v[8][4];
@@ -314,125 +334,142 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + rs;
             const float4 t = *reinterpret_cast<const float4*>(epi + rl * 32 + ((cg ^ (rl & 7)) << 2));
-            v[it][0] = t.x + b4[c].x; v[it][1] = t.y + b4[c].y;
-            v[it][2] = t.z + b4[c].z; v[it][3] = t.w + b4[c].w;
+            v[it][0] = t.x + b4.x; v[it][1] = t.y + b4.y;
+            v[it][2] = t.z + b4.z; v[it][3] = t.w + b4.w;
           }
-          if (p.out2) {
+          if constexpr (EPI & F_OUT2) {
+            if (p.out2) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (ok[it]) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(v[it][0], v[it][1]);
-                __nv_bfloat162 hi = __floats2bfloat162_rn(v[it][2], v[it][3]);
-                uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                *reinterpret_cast<uint2*>(p.out2 + (row0 + it * 4) * p.ldo2 + col) = pk;
-              }
+              for (int it = 0; it < 8; ++it)
+                if (ok[it]) {
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(v[it][0], v[it][1]);
+                  __nv_bfloat162 hi = __floats2bfloat162_rn(v[it][2], v[it][3]);
+                  uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                  *reinterpret_cast<uint2*>(p.out2 + (row0 + it * 4) * p.ldo2 + col) = pk;
+                }
+            }
           }
-          if (p.act == MMTG_ACT_TANH) {
+          if constexpr (EPI & F_ACT) {
+            if (p.act == MMTG_ACT_TANH) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
+              for (int it = 0; it < 8; ++it)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[it][e] = tanh_fast(v[it][e]);
-          } else if (p.act == MMTG_ACT_GELU_NEW) {
+                for (int e = 0; e < 4; ++e) v[it][e] = tanh_fast(v[it][e]);
+            } else if (p.act == MMTG_ACT_GELU_NEW) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
+              for (int it = 0; it < 8; ++it)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[it][e] = gelu_new_fast(v[it][e]);
+                for (int e = 0; e < 4; ++e) v[it][e] = gelu_new_fast(v[it][e]);
+            }
           }
-          if (p.dgelu_src) {
+          if constexpr (EPI & F_DACT) {
+            if (p.dgelu_src) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].x));
-              const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].y));
-              if (p.dact_tanh_out) {
-                v[it][0] *= 1.f - a.x * a.x; v[it][1] *= 1.f - a.y * a.y;
-                v[it][2] *= 1.f - b.x * b.x; v[it][3] *= 1.f - b.y * b.y;
-              } else {
-                v[it][0] *= dgelu_new_fast(a.x); v[it][1] *= dgelu_new_fast(a.y);
-                v[it][2] *= dgelu_new_fast(b.x); v[it][3] *= dgelu_new_fast(b.y);
+              for (int it = 0; it < 8; ++it) {
+                const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].x));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].y));
+                if (p.dact_tanh_out) {
+                  v[it][0] *= 1.f - a.x * a.x; v[it][1] *= 1.f - a.y * a.y;
+                  v[it][2] *= 1.f - b.x * b.x; v[it][3] *= 1.f - b.y * b.y;
+                } else {
+                  v[it][0] *= dgelu_new_fast(a.x); v[it][1] *= dgelu_new_fast(a.y);
+                  v[it][2] *= dgelu_new_fast(b.x); v[it][3] *= dgelu_new_fast(b.y);
+                }
               }
             }
           }
-          if (p.residual) {
+          if constexpr (EPI & F_RES) {
+            if (p.residual) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              v[it][0] += res[it].x; v[it][1] += res[it].y; v[it][2] += res[it].z; v[it][3] += res[it].w;
+              for (int it = 0; it < 8; ++it) {
+                v[it][0] += res[it].x; v[it][1] += res[it].y; v[it][2] += res[it].z; v[it][3] += res[it].w;
+              }
             }
           }
-          if (p.rowtab0) {
+          if constexpr (EPI & F_ROWTAB) {
+            if (p.rowtab0) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (ok[it]) {
-                const long long row = row0 + it * 4;
-                const long long ti = p.rowidx0 ? (long long)__ldg(p.rowidx0 + row) : (long long)(row % p.rowmod0);
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.rowtab0 + ti * p.ldt0 + col));
-                v[it][0] += t.x; v[it][1] += t.y; v[it][2] += t.z; v[it][3] += t.w;
-              }
-          }
-          if (p.rowtab1) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (ok[it]) {
-                const long long ti = (long long)__ldg(p.rowidx1 + row0 + it * 4);
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.rowtab1 + ti * p.ldt1 + col));
-                v[it][0] += t.x; v[it][1] += t.y; v[it][2] += t.z; v[it][3] += t.w;
-              }
-          }
-          if (p.colsum) {
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (ok[it]) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) s4[e] += v[it][e];
-              }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 8);
-              s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 16);
+              for (int it = 0; it < 8; ++it)
+                if (ok[it]) {
+                  const long long row = row0 + it * 4;
+                  const long long ti = p.rowidx0 ? (long long)__ldg(p.rowidx0 + row) : (long long)(row % p.rowmod0);
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(p.rowtab0 + ti * p.ldt0 + col));
+                  v[it][0] += t.x; v[it][1] += t.y; v[it][2] += t.z; v[it][3] += t.w;
+                }
             }
-            if (rs == 0 && colok) {
+            if (p.rowtab1) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) atomicAdd(p.colsum + col + e, s4[e]);
+              for (int it = 0; it < 8; ++it)
+                if (ok[it]) {
+                  const long long ti = (long long)__ldg(p.rowidx1 + row0 + it * 4);
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(p.rowtab1 + ti * p.ldt1 + col));
+                  v[it][0] += t.x; v[it][1] += t.y; v[it][2] += t.z; v[it][3] += t.w;
+                }
             }
           }
-          if (p.atomic) {
+          if constexpr (EPI & F_COLSUM) {
+            if (p.colsum) {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (ok[it]) {
-                float* dstp = (float*)p.out + (row0 + it * 4) * p.ldo + col;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstp),
-                             "f"(v[it][0]), "f"(v[it][1]), "f"(v[it][2]), "f"(v[it][3])
-                             : "memory");
-              }
-          } else if (p.out_bf16) {
+              for (int it = 0; it < 8; ++it)
+                if (ok[it]) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (ok[it]) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(v[it][0], v[it][1]);
-                __nv_bfloat162 hi = __floats2bfloat162_rn(v[it][2], v[it][3]);
-                uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                *reinterpret_cast<uint2*>((bf16*)p.out + (row0 + it * 4) * p.ldo + col) = pk;
+                  for (int e = 0; e < 4; ++e) s4[e] += v[it][e];
+                }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 8);
+                s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 16);
               }
+              if (rs == 0 && colok) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) atomicAdd(p.colsum + col + e, s4[e]);
+              }
+            }
+          }
+          bool do_atomic = false;
+          if constexpr (EPI & F_ATOMIC) do_atomic = p.atomic != 0;
+          if (do_atomic) {
+            if constexpr (EPI & F_ATOMIC) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (ok[it]) {
+                  float* dstp = (float*)p.out + (row0 + it * 4) * p.ldo + col;
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstp),
+                               "f"(v[it][0]), "f"(v[it][1]), "f"(v[it][2]), "f"(v[it][3])
+                               : "memory");
+                }
+            }
           } else {
+            if (p.out_bf16) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (ok[it])
-                *reinterpret_cast<float4*>((float*)p.out + (row0 + it * 4) * p.ldo + col) =
-                    make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
+              for (int it = 0; it < 8; ++it)
+                if (ok[it]) {
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(v[it][0], v[it][1]);
+                  __nv_bfloat162 hi = __floats2bfloat162_rn(v[it][2], v[it][3]);
+                  uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                  *reinterpret_cast<uint2*>((bf16*)p.out + (row0 + it * 4) * p.ldo + col) = pk;
+                }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (ok[it])
+                  *reinterpret_cast<float4*>((float*)p.out + (row0 + it * 4) * p.ldo + col) =
+                      make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
+            }
           }
         } else {
           // phase 2 (scalar; unaligned pitches such as the contiguous [.., 13317] logits):
           // lane = column -> every store instruction writes 128 contiguous bytes of one row.
-          // Supports bias / act / residual / colsum.
           const int scol = col0 + lane;
           const bool scolok = scol < p.N;
           const int nrows = min(32, p.M - row_base);  // warp-uniform, may be <= 0
           const int sw = lane >> 2, sl = lane & 3;    // swizzled position of this lane's column
-          float csum = 0.f;
-          if (p.out_bf16 || p.atomic || p.residual || p.act != MMTG_ACT_NONE || p.colsum) {
+          if constexpr (EPI & (F_ACT | F_RES | F_COLSUM | F_ATOMIC)) {
+            float csum = 0.f;
             for (int rr = 0; rr < nrows; ++rr) {
               const long long row = row_base + rr;
-              float v = epi[rr * 32 + ((sw ^ (rr & 7)) << 2) + sl] + bs[c];
+              float v = epi[rr * 32 + ((sw ^ (rr & 7)) << 2) + sl] + bs;
               if (scolok) {
                 if (p.act == MMTG_ACT_TANH) v = tanh_fast(v);
                 else if (p.act == MMTG_ACT_GELU_NEW) v = gelu_new_fast(v);
@@ -445,27 +482,40 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             }
             if (p.colsum && scolok && nrows > 0) atomicAdd(p.colsum + scol, csum);
           } else {
-            // lean path: fp32 store (+bias) only — the lm_head logits
-            float* orow = (float*)p.out + (long long)row_base * p.ldo + scol;
+            // lean path: store (+bias) only — the lm_head logits
+            if (p.out_bf16) {
+              bf16* orow = (bf16*)p.out + (long long)row_base * p.ldo + scol;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-              const float v = epi[rr * 32 + ((sw ^ (rr & 7)) << 2) + sl] + bs[c];
-              if (rr < nrows && scolok) orow[(long long)rr * p.ldo] = v;
+              for (int rr = 0; rr < 32; ++rr) {
+                const float v = epi[rr * 32 + ((sw ^ (rr & 7)) << 2) + sl] + bs;
+                if (rr < nrows && scolok) orow[(long long)rr * p.ldo] = __float2bfloat16(v);
+              }
+            } else {
+              float* orow = (float*)p.out + (long long)row_base * p.ldo + scol;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const float v = epi[rr * 32 + ((sw ^ (rr & 7)) << 2) + sl] + bs;
+                if (rr < nrows && scolok) orow[(long long)rr * p.ldo] = v;
+              }
             }
           }
         }
+        b4 = b4n;
+        bs = bsn;
         __syncwarp();
       }
-      if (p.lse_partial) {
-        // the two column halves of a 128/256-wide tile keep separate partial slots
-        const long long row = row_base + lane;
-        if (row < p.M) {
-          float* dst = p.lse_partial + ((long long)(n_t * 2 + half) * p.M + row) * 2;
-          dst[0] = run_max;
-          dst[1] = run_sum;
+      if constexpr (EPI & F_LSE) {
+        if (p.lse_partial) {
+          // the two column halves of a 128/256-wide tile keep separate partial slots
+          const long long row = row_base + lane;
+          if (row < p.M) {
+            float* dst = p.lse_partial + ((long long)(n_t * 2 + half) * p.M + row) * 2;
+            dst[0] = run_max;
+            dst[1] = run_sum;
+          }
         }
       }
-      if (n0 >= p.N) {
+      if (!released) {
         // this half-tile lies entirely beyond N: nothing was read, still release the accumulator
         tc_fence_before();
         __syncwarp();
@@ -568,13 +618,13 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
 
 void count_launch(int n = 1);
 
-template <int BN>
+template <int BN, uint32_t EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        cudaStream_t st) {
   using C = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    MMTG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+    MMTG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
@@ -596,7 +646,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN>, tmA, tmB, p));
+  MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI>, tmA, tmB, p));
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;
@@ -666,6 +716,32 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   else         MMTG_TRY(make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, 64));
 
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 256) return launch_gemm<256>(tmA, tmB, p, st);
-  return launch_gemm<128>(tmA, tmB, p, st);
+  // pick the smallest instantiated epilogue that covers the requested features
+  uint32_t need = 0;
+  if (p.out2) need |= F_OUT2;
+  if (p.act != MMTG_ACT_NONE) need |= F_ACT;
+  if (p.dgelu_src) need |= F_DACT;
+  if (p.residual) need |= F_RES;
+  if (p.rowtab0 || p.rowtab1) need |= F_ROWTAB;
+  if (p.colsum) need |= F_COLSUM;
+  if (p.atomic) need |= F_ATOMIC;
+  if (p.lse_partial) need |= F_LSE;
+  if (!p.vec4) need |= F_SCALAR;
+#define MMTG_TRY_EPI(MASK)                                         \
+  if ((need & ~(uint32_t)(MASK)) == 0) {                           \
+    if (BN == 256) return launch_gemm<256, (MASK)>(tmA, tmB, p, st); \
+    return launch_gemm<128, (MASK)>(tmA, tmB, p, st);              \
+  }
+  MMTG_TRY_EPI(0u)
+  MMTG_TRY_EPI(F_ACT | F_OUT2)
+  MMTG_TRY_EPI(F_RES)
+  MMTG_TRY_EPI(F_DACT | F_COLSUM)
+  MMTG_TRY_EPI(F_ATOMIC)
+  MMTG_TRY_EPI(F_ROWTAB)
+  MMTG_TRY_EPI(F_SCALAR | F_LSE)
+  MMTG_TRY_EPI(F_SCALAR | F_ACT | F_RES | F_COLSUM | F_ATOMIC)
+  MMTG_TRY_EPI(F_OUT2 | F_ACT | F_DACT | F_RES | F_ROWTAB | F_COLSUM | F_ATOMIC | F_LSE)
+#undef MMTG_TRY_EPI
+  set_last_error("no GEMM epilogue instantiation covers feature mask 0x%x", need);
+  return -1;
 }

@@ -9,7 +9,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y
                   float* mean, float* rstd, int M, int E, float eps, cudaStream_t st);
 int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd,
                   const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
-                  int M, int E, cudaStream_t st);
+                  bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st);
 int cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
 int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc, float* out, int M,
            int N, cudaStream_t st);

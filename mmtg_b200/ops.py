@@ -82,11 +82,11 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, want_bf16=True, want_f32=False):
     return y16, y32, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx16=None, dx_colsum=None):
     M, E = x.shape
     _lib.check(_lib.lib().mmtg_layernorm_bwd(_p(dy), int(dy.dtype == torch.bfloat16), _p(x), _p(mean), _p(rstd),
-                                             _p(gamma), _p(dx), int(accumulate), _p(dgamma), _p(dbeta), M, E,
-                                             _st()), "mmtg_layernorm_bwd")
+                                             _p(gamma), _p(dx), int(accumulate), _p(dgamma), _p(dbeta),
+                                             _p(dx16), _p(dx_colsum), M, E, _st()), "mmtg_layernorm_bwd")
 
 
 def colsum(x, out, copy16=None):

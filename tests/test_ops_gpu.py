@@ -28,8 +28,12 @@ def test_layernorm_fwd_bwd(cuda, M, E):
         base = torch.randn(M, E, generator=g, device=cuda)
         dx = base.clone()
         dg, db = torch.zeros(E, device=cuda), torch.zeros(E, device=cuda)
-        ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, True, dg, db)
+        dx16 = torch.empty(M, E, device=cuda, dtype=torch.bfloat16)
+        cs = torch.zeros(E, device=cuda)
+        ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, True, dg, db, dx16, cs)
         assert torch.allclose(dx - base, xr.grad, atol=2e-5, rtol=1e-4)
+        assert torch.equal(dx16, dx.to(torch.bfloat16))
+        assert torch.allclose(cs, dx.sum(0), atol=1e-3 * math.sqrt(M), rtol=1e-4)
         assert torch.allclose(dg, gr.grad, atol=1e-3 * math.sqrt(M), rtol=1e-4)
         assert torch.allclose(db, br.grad, atol=1e-3 * math.sqrt(M), rtol=1e-4)
 
