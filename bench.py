@@ -173,7 +173,7 @@ def main():
     # L2 flush buffer (> 126 MB); the step's own working set (~3 GB of activations) already exceeds L2
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(batch):
+    def eager_step(batch):
         hf, kl, logits = model(batch)
         loss = crit(logits, batch["targets"], batch["rating"], STAGE)
         total = loss.mean() + ALPHA * kl.mean()
@@ -181,6 +181,15 @@ def main():
         opt.step()
         opt.zero_grad()
         return total
+
+    # fixed shapes -> the whole step is replayed from one CUDA graph (launch-bound otherwise);
+    # MMTG_GRAPH=0 falls back to eager launches. Multi-GPU keeps eager launches this round.
+    use_graph = os.environ.get("MMTG_GRAPH", "1" if world == 1 else "0") == "1"
+    if use_graph:
+        from mmtg_b200.graph import GraphedTrainStep
+        step = GraphedTrainStep(model, crit, opt, resident, alpha=ALPHA, stage=STAGE, warmup=3)
+    else:
+        step = eager_step
 
     def barrier():
         if world > 1:
@@ -207,15 +216,19 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = ms.item()
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss.item() ----
+    def e2e_step():
+        if use_graph:  # pinned host -> static device buffers (async H2D) -> replay
+            return step(pinned)
+        return step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()})
+
     for _ in range(2):
-        step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}).item()
+        e2e_step().item()
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(K):
-        batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        step(batch).item()
+        e2e_step().item()
     e3.record()
     barrier()
     e2e_wall = time.perf_counter() - t0
@@ -229,9 +242,9 @@ def main():
     lib.mmtg_prof_reset()
     lib.mmtg_prof_enable(1)
     PROF_STEPS = 2
-    for _ in range(PROF_STEPS):
+    for _ in range(PROF_STEPS):  # profiled steps always launch eagerly (events per launch)
         flush.zero_()
-        step(resident)
+        eager_step(resident)
     torch.cuda.synchronize()
     lib.mmtg_prof_enable(0)
     classes = {}
@@ -240,6 +253,8 @@ def main():
         lib.mmtg_prof_collect(cls, C.byref(t), C.byref(f), C.byref(b), C.byref(n))
         classes[name] = {"ms_per_step": t.value / PROF_STEPS, "launches_per_step": n.value // PROF_STEPS,
                          "gflop_per_step": f.value / PROF_STEPS / 1e9, "gbytes_per_step": b.value / PROF_STEPS / 1e9}
+    if os.environ.get("MMTG_PROF_DUMP"):
+        lib.mmtg_prof_dump(os.environ["MMTG_PROF_DUMP"].encode())
     lib.mmtg_prof_reset()
     pk, pk_src = peaks()
     gemm = classes["gemm_tcgen05"]
@@ -257,6 +272,7 @@ def main():
             "config": {"workload": "MMTG train step (fwd + MyLoss stage 3 + 0.2*KL, bwd, clip 1.0, AdamW) bf16 GEMMs / fp32 master+residual, batch 32 per GPU, L=236, V=13317 (BASELINE.json configs[1]); dropout p=0",
                        "global_batch": global_batch, "seq_len": 236,
                        "parallelism": f"dp{world}" if world > 1 else "single",
+                       "launch": "cuda_graph" if use_graph else "eager",
                        "l2": "working set (~3 GB activations/step) exceeds L2; 256 MB flush before profiled steps"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms.item() / K},

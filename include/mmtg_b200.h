@@ -35,6 +35,7 @@ int64_t mmtg_launch_count(void);
 void mmtg_prof_enable(int32_t on);
 void mmtg_prof_reset(void);
 int mmtg_prof_collect(int32_t cls, double* ms, double* flops, double* bytes, int64_t* count);
+int mmtg_prof_dump(const char* csv_path);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05/TMEM fed by TMA:  out = epilogue(A · Bᵀ)
@@ -89,9 +90,12 @@ typedef struct mmtg_gemm_args {
    * layout [2*ceil(N/block_n)][M][2] fp32 — lets the loss kernels skip a full re-read of logits */
   float* lse_partial;
   /* 0: dgelu_src holds the pre-activation u, value *= gelu_new'(u);
-   * 1: dgelu_src holds a tanh OUTPUT y, value *= (1 - y*y)   (projector backward) */
+   * 1: dgelu_src holds a tanh OUTPUT y, value *= (1 - y*y)   (projector backward);
+   * 2: dgelu_src holds the activation derivative itself, value *= src */
   int32_t dact_tanh_out;
-  int32_t _pad2;
+  /* 0: out2 receives the pre-activation value; 1 (with MMTG_ACT_GELU_NEW): out2 receives
+   * gelu_new'(pre-activation), so the backward epilogue is a single multiply */
+  int32_t out2_mode;
 } mmtg_gemm_args;
 
 int mmtg_gemm_bf16(const mmtg_gemm_args* args, void* stream);
@@ -239,10 +243,12 @@ int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_
  * ------------------------------------------------------------------------------------------ */
 int mmtg_grad_norm_sq(const float* grads, int64_t n, float* partial_ws, int32_t partial_len,
                       float* out_normsq, void* stream);
+/* lr_dev / step_dev (optional, device): learning rate and 0-based step counter kept on the device
+ * (the counter is bumped after the update) so the call can be replayed from a CUDA graph. */
 int mmtg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     void* params_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int32_t step, int32_t correct_bias, const float* normsq,
-                    float max_norm, void* stream);
+                    float max_norm, const float* lr_dev, int32_t* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

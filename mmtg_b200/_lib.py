@@ -38,7 +38,7 @@ class GemmArgs(C.Structure):
         ("rowtab1", C.c_void_p), ("rowidx1", C.c_void_p), ("ldt1", C.c_int64),
         ("colsum", C.c_void_p),
         ("lse_partial", C.c_void_p),
-        ("dact_tanh_out", C.c_int32), ("_pad2", C.c_int32),
+        ("dact_tanh_out", C.c_int32), ("out2_mode", C.c_int32),
     ]
 
 

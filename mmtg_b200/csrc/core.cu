@@ -68,6 +68,21 @@ extern "C" const char* mmtg_last_error(void) { return mmtg::get_last_error(); }
 extern "C" int mmtg_abi_version(void) { return MMTG_ABI_VERSION; }
 extern "C" int64_t mmtg_launch_count(void) { return (int64_t)mmtg::g_launches.load(); }
 
+// Writes one CSV line per recorded launch: class, ms, flops, bytes (diagnostics for profiles/).
+extern "C" int mmtg_prof_dump(const char* path) {
+  std::lock_guard<std::mutex> lk(mmtg::g_prof_mu);
+  FILE* f = fopen(path, "w");
+  if (!f) return -1;
+  fprintf(f, "class,ms,flops,bytes\n");
+  for (auto& s : mmtg::g_slots) {
+    float e = 0.f;
+    if (cudaEventSynchronize(s.e1) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&e, s.e0, s.e1) != cudaSuccess) continue;
+    fprintf(f, "%d,%.6f,%.0f,%.0f\n", s.cls, e, s.flops, s.bytes);
+  }
+  fclose(f);
+  return 0;
+}
 extern "C" void mmtg_prof_enable(int32_t on) { mmtg::g_prof_on = on != 0; }
 extern "C" void mmtg_prof_reset(void) {
   std::lock_guard<std::mutex> lk(mmtg::g_prof_mu);

@@ -74,95 +74,89 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 // in shared memory and added to global with one atomic per column per block.
 // ------------------------------------------------------------------------------------------
 template <int E, bool DY_BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(E / 2)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, float* __restrict__ dx, int accumulate_dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ dx16,
               float* __restrict__ dx_colsum, int M) {
-  constexpr int V = E / 128;
-  __shared__ float s_dg[E], s_db[E], s_cs[E];
-  for (int i = threadIdx.x; i < E; i += blockDim.x) s_dg[i] = s_db[i] = s_cs[i] = 0.f;
-  __syncthreads();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int l = lane_id();
-  float4 gam[V], adg[V], adb[V], acs[V];
+  // Two passes over a tile of TR rows (second pass re-reads from L1/L2):
+  //   1. warp per row: m1 = mean(g), m2 = mean(g * xhat), g = dy * gamma   -> shared memory
+  //   2. thread per column pair: dx for every row of the tile, column sums in 6 registers
+  // (row-wise accumulators cost 72 registers / 8 warps per SM; shared atomics were LSU-bound.)
+  constexpr int NT = E / 2, NW = NT / 32, TR = 2 * NW, V = E / 128;
+  __shared__ float s_m1[TR], s_m2[TR], s_mu[TR], s_rs[TR];
+  const int warp = threadIdx.x >> 5, l = lane_id();
+  const int c = threadIdx.x * 2;
+  const float2 gam2 = *reinterpret_cast<const float2*>(gamma + c);
+  float2 adg = make_float2(0.f, 0.f), adb = adg, acs = adg;
+  const int ntiles = cdiv(M, TR);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * TR;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + l + i * 32);
-    adg[i] = adb[i] = acs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int row = warp; row < M; row += nwarps) {
-    const float mu = mean[row], rs = rstd[row];
-    float4 xh[V], dyv[V];
-    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < 2; ++k) {
+      const int rl = warp * 2 + k, row = r0 + rl;
+      if (row < M) {
+        const float mu = mean[row], rs = rstd[row];
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int c4 = l + i * 32;
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)row * E) + c4);
-      if (DY_BF16) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>((const bf16*)dy_ + (long long)row * E) + c4);
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-        dyv[i] = make_float4(a.x, a.y, b.x, b.y);
-      } else {
-        dyv[i] = __ldg(reinterpret_cast<const float4*>((const float*)dy_ + (long long)row * E) + c4);
+        for (int i = 0; i < V; ++i) {
+          const int c4 = l + i * 32;
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)row * E) + c4);
+          float4 dyv;
+          if (DY_BF16) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>((const bf16*)dy_ + (long long)row * E) + c4);
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            dyv = make_float4(a.x, a.y, b.x, b.y);
+          } else {
+            dyv = __ldg(reinterpret_cast<const float4*>((const float*)dy_ + (long long)row * E) + c4);
+          }
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+          const float g0 = dyv.x * gm.x, g1 = dyv.y * gm.y, g2 = dyv.z * gm.z, g3 = dyv.w * gm.w;
+          s1 += g0 + g1 + g2 + g3;
+          s2 += g0 * (xv.x - mu) + g1 * (xv.y - mu) + g2 * (xv.z - mu) + g3 * (xv.w - mu);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2) * rs;
+        if (l == 0) {
+          s_m1[rl] = s1 * (1.f / E);
+          s_m2[rl] = s2 * (1.f / E);
+          s_mu[rl] = mu;
+          s_rs[rl] = rs;
+        }
       }
-      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      const float4 g = make_float4(dyv[i].x * gam[i].x, dyv[i].y * gam[i].y, dyv[i].z * gam[i].z,
-                                   dyv[i].w * gam[i].w);
-      s1 += g.x + g.y + g.z + g.w;
-      s2 += g.x * xh[i].x + g.y * xh[i].y + g.z * xh[i].z + g.w * xh[i].w;
-      adg[i].x += dyv[i].x * xh[i].x; adg[i].y += dyv[i].y * xh[i].y;
-      adg[i].z += dyv[i].z * xh[i].z; adg[i].w += dyv[i].w * xh[i].w;
-      adb[i].x += dyv[i].x; adb[i].y += dyv[i].y; adb[i].z += dyv[i].z; adb[i].w += dyv[i].w;
     }
-    const float m1 = warp_sum(s1) * (1.f / E), m2 = warp_sum(s2) * (1.f / E);
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int c4 = l + i * 32;
-      float4 o;
-      o.x = rs * (dyv[i].x * gam[i].x - m1 - xh[i].x * m2);
-      o.y = rs * (dyv[i].y * gam[i].y - m1 - xh[i].y * m2);
-      o.z = rs * (dyv[i].z * gam[i].z - m1 - xh[i].z * m2);
-      o.w = rs * (dyv[i].w * gam[i].w - m1 - xh[i].w * m2);
-      float4* dst = reinterpret_cast<float4*>(dx + (long long)row * E) + c4;
+    __syncthreads();
+    const int nr = min(TR, M - r0);
+#pragma unroll 4
+    for (int rl = 0; rl < nr; ++rl) {
+      const long long off = (long long)(r0 + rl) * E + c;
+      float2 dyv;
+      if (DY_BF16) dyv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>((const bf16*)dy_ + off));
+      else dyv = *reinterpret_cast<const float2*>((const float*)dy_ + off);
+      const float2 xv = *reinterpret_cast<const float2*>(x + off);
+      const float mu = s_mu[rl], rs = s_rs[rl], m1 = s_m1[rl], m2 = s_m2[rl];
+      const float xh0 = (xv.x - mu) * rs, xh1 = (xv.y - mu) * rs;
+      float2 o;
+      o.x = rs * (dyv.x * gam2.x - m1 - xh0 * m2);
+      o.y = rs * (dyv.y * gam2.y - m1 - xh1 * m2);
       if (accumulate_dx) {
-        const float4 old = *dst;
-        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        const float2 old = *reinterpret_cast<const float2*>(dx + off);
+        o.x += old.x;
+        o.y += old.y;
       }
-      *dst = o;
-      if (dx16) {  // bf16 copy of the (accumulated) residual-stream gradient: next GEMM operand
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-        reinterpret_cast<uint2*>(dx16 + (long long)row * E)[c4] =
-            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-      }
-      acs[i].x += o.x; acs[i].y += o.y; acs[i].z += o.z; acs[i].w += o.w;
+      *reinterpret_cast<float2*>(dx + off) = o;
+      if (dx16) *reinterpret_cast<__nv_bfloat162*>(dx16 + off) = __floats2bfloat162_rn(o.x, o.y);
+      adg.x += dyv.x * xh0; adg.y += dyv.y * xh1;
+      adb.x += dyv.x; adb.y += dyv.y;
+      acs.x += o.x; acs.y += o.y;
     }
+    __syncthreads();
   }
-  if (dx_colsum) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int c = (l + i * 32) * 4;
-      atomicAdd(&s_cs[c], acs[i].x); atomicAdd(&s_cs[c + 1], acs[i].y);
-      atomicAdd(&s_cs[c + 2], acs[i].z); atomicAdd(&s_cs[c + 3], acs[i].w);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int c = (l + i * 32) * 4;
-    atomicAdd(&s_dg[c], adg[i].x); atomicAdd(&s_dg[c + 1], adg[i].y);
-    atomicAdd(&s_dg[c + 2], adg[i].z); atomicAdd(&s_dg[c + 3], adg[i].w);
-    atomicAdd(&s_db[c], adb[i].x); atomicAdd(&s_db[c + 1], adb[i].y);
-    atomicAdd(&s_db[c + 2], adb[i].z); atomicAdd(&s_db[c + 3], adb[i].w);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + i, s_dg[i]);
-    if (dbeta) atomicAdd(dbeta + i, s_db[i]);
-    if (dx_colsum) atomicAdd(dx_colsum + i, s_cs[i]);
-  }
+  if (dgamma) { atomicAdd(dgamma + c, adg.x); atomicAdd(dgamma + c + 1, adg.y); }
+  if (dbeta) { atomicAdd(dbeta + c, adb.x); atomicAdd(dbeta + c + 1, adb.y); }
+  if (dx_colsum) { atomicAdd(dx_colsum + c, acs.x); atomicAdd(dx_colsum + c + 1, acs.y); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -356,9 +350,10 @@ int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean
                   const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
                   bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st) {
   MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
-  const int blocks = min(cdiv(M, 8), num_sms() * 2);
+  const int tile_rows = 2 * (E / 64);
+  const int blocks = min(cdiv(M, tile_rows), num_sms() * 4);
   ProfScope prof(2, 0, (double)M * E * (4 + (dy_bf16 ? 2 : 4) + 4 + (accumulate_dx ? 4 : 0) + (dx16 ? 2 : 0)), st);
-#define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, dx16, dx_colsum, M)
+#define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, EE / 2, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, dx16, dx_colsum, M)
   if (E == 768) { if (dy_bf16) LNB(768, true); else LNB(768, false); }
   else { if (dy_bf16) LNB(512, true); else LNB(512, false); }
 #undef LNB

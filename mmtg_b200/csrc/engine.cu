@@ -32,7 +32,7 @@ struct LayerWs {
   float* h_mid;
   bf16* x2;
   float *mean2, *rstd2;
-  bf16 *u, *a;
+  bf16 *u, *a;  // u = gelu_new'(pre-activation) (saved derivative), a = gelu_new(pre-activation)
   float* h_out;
 };
 
@@ -201,6 +201,8 @@ struct Gemm {
   Gemm& residual(const float* r, long long ld) { a.residual = r; a.ldr = ld; return *this; }
   Gemm& dgelu(const bf16* u, long long ld) { a.dgelu_src = u; a.ldg = ld; return *this; }
   Gemm& dtanh(const bf16* y, long long ld) { a.dgelu_src = y; a.ldg = ld; a.dact_tanh_out = 1; return *this; }
+  Gemm& dmul(const bf16* d, long long ld) { a.dgelu_src = d; a.ldg = ld; a.dact_tanh_out = 2; return *this; }
+  Gemm& out2_deriv(bf16* o, long long ld) { a.out2 = o; a.ldo2 = ld; a.out2_mode = 1; return *this; }
   Gemm& colsum(float* c) { a.colsum = c; return *this; }
   Gemm& accumulate(int split = 1) { a.accumulate = 1; a.split_k = split; return *this; }
   Gemm& lse(float* p, int bn) { a.lse_partial = p; a.block_n = bn; return *this; }
@@ -352,7 +354,7 @@ extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void
                  .out_f32(L.h_mid, E).bias(P + lo.proj_b).residual(L.h_in, E).run(st));
     MMTG_TRY(layernorm_fwd(L.h_mid, P + lo.ln2_w, P + lo.ln2_b, L.x2, nullptr, L.mean2, L.rstd2, M, E, eps, st));
     MMTG_TRY(Gemm(L.x2, E, false, W + lo.fc_w, 4 * E, true, M, 4 * E, E)
-                 .out_bf16(L.a, 4 * E).out2(L.u, 4 * E).bias(P + lo.fc_b).act(MMTG_ACT_GELU_NEW).run(st));
+                 .out_bf16(L.a, 4 * E).out2_deriv(L.u, 4 * E).bias(P + lo.fc_b).act(MMTG_ACT_GELU_NEW).run(st));
     MMTG_TRY(Gemm(L.a, 4 * E, false, W + lo.proj2_w, E, true, M, E, 4 * E)
                  .out_f32(L.h_out, E).bias(P + lo.proj2_b).residual(L.h_mid, E).run(st));
   }
@@ -400,7 +402,7 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       const mmtg_layer_offsets& lo = o.layer[l];
       // ---- MLP ---- (g16 = bf16(dh) and d(proj2_b) were produced by the LayerNorm backward above)
       MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj2_w, E, false, M, 4 * E, E)
-                   .out_bf16(w.du, 4 * E).dgelu(L.u, 4 * E).colsum(G + lo.fc_b).run(st));
+                   .out_bf16(w.du, 4 * E).dmul(L.u, 4 * E).colsum(G + lo.fc_b).run(st));
       MMTG_TRY(wgrad(L.a, 4 * E, w.g16, E, G + lo.proj2_w, E, 4 * E, E, M, st));
       MMTG_TRY(Gemm(w.du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(w.dx, E).run(st));
       MMTG_TRY(wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, st));

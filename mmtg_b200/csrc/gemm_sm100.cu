@@ -19,6 +19,7 @@
 //    fused bias / tanh / gelu_new / dgelu / residual / row-gather adds / column sums / split-K
 //    atomics / per-row log-sum-exp partials.
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 
@@ -55,16 +56,21 @@ struct GemmParams {
   float* lse_partial;
   int vec4;
   int dact_tanh_out;
+  int out2_mode;
 };
 
-template <int BN>
+// TWO = cta_group::2: the pair's 256 x BN tile is ONE MMA; each CTA stages its own 128 A rows and
+// only HALF of the B tile (the tensor core reads the other half from the peer SM), which halves
+// the shared-memory write+read traffic per FLOP — the 1-SM kernel is smem-bandwidth bound at
+// ~2/3 of the tensor peak (12 KB operand reads + 12 KB TMA writes per 128-cycle MMA).
+template <int BN, bool TWO>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (232448 - 8 * 32 * 32 * 4 - 256 - 1024) / STAGE_BYTES;
   static constexpr int EPI_PITCH = 32;  // floats; XOR-swizzled 16-B chunks, no padding
   static constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH;
   static constexpr int EPI_BYTES = 8 * EPI_WARP_FLOATS * 4;
@@ -80,11 +86,11 @@ enum : uint32_t {
   F_LSE = 128, F_SCALAR = 256
 };
 
-template <int BN, uint32_t EPI>
+template <int BN, uint32_t EPI, bool TWO>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, TWO>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-B alignment; offset (not cast) keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -101,11 +107,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 2);  // MMA commits of both CTAs of the pair (multicast arrivals)
+      // 1-SM mode: MMA commits of both CTAs of the pair (multicast arrivals);
+      // 2-SM mode: the leader's single commit, multicast to both CTAs
+      mbar_init(&empty[s], TWO ? 1 : 2);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);
+      mbar_init(&tempty[a], TWO ? 16 : 8);  // 2-SM: both CTAs' epilogue warps release the leader
     }
     fence_barrier_init();
   }
@@ -114,8 +122,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (TWO) {
+      tmem_alloc2(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -139,27 +152,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait<1>(&empty[s], ph ^ 1);
         if (lane == 0) {
           uint8_t* sA = smem + s * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
-          // A tile (own) + the whole B tile: half from this CTA, half multicast by the peer
-          mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
-          if (!p.a_mn) {
-            tma_load_2d(sA, &tmA, &full[s], kb * C::BK, m0);
-          } else {
+          if (TWO) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects all four boxes
+            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d_2sm(sA, &tmA, &full[s], kb * C::BK, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < C::BM / 64; ++j)
-              tma_load_2d(sA + j * 8192, &tmA, &full[s], m0 + 64 * j, kb * C::BK);
-          }
-          if (!p.b_mn) {  // rows [crank*BN/2, +BN/2) of the B tile -> both CTAs
-            tma_load_2d_mc(sB + crank * (C::B_BYTES / 2), &tmB, &full[s], kb * C::BK,
-                           n0 + (int)crank * (BN / 2), (uint16_t)3);
-          } else {
+              for (int j = 0; j < C::BM / 64; ++j)
+                tma_load_2d_2sm(sA + j * 8192, &tmA, &full[s], m0 + 64 * j, kb * C::BK);
+            }
+            if (!p.b_mn) {  // this CTA's half of the B tile: rows [crank*BN/2, +BN/2)
+              tma_load_2d_2sm(sB, &tmB, &full[s], kb * C::BK, n0 + (int)crank * (BN / 2));
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 128; ++j) {
-              const int jj = (int)crank * (BN / 128) + j;
-              tma_load_2d_mc(sB + jj * 8192, &tmB, &full[s], n0 + 64 * jj, kb * C::BK, (uint16_t)3);
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_2d_2sm(sB + j * 8192, &tmB, &full[s], n0 + (int)crank * (BN / 2) + 64 * j,
+                                kb * C::BK);
+            }
+          } else {
+            // A tile (own) + the whole B tile: half from this CTA, half multicast by the peer
+            mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d(sA, &tmA, &full[s], kb * C::BK, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < C::BM / 64; ++j)
+                tma_load_2d(sA + j * 8192, &tmA, &full[s], m0 + 64 * j, kb * C::BK);
+            }
+            if (!p.b_mn) {  // rows [crank*BN/2, +BN/2) of the B tile -> both CTAs
+              tma_load_2d_mc(sB + crank * (C::B_BYTES / 2), &tmB, &full[s], kb * C::BK,
+                             n0 + (int)crank * (BN / 2), (uint16_t)3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = (int)crank * (BN / 128) + j;
+                tma_load_2d_mc(sB + jj * 8192, &tmB, &full[s], n0 + 64 * jj, kb * C::BK, (uint16_t)3);
+              }
             }
           }
         }
@@ -170,9 +203,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(C::BM, BN, p.a_mn, p.b_mn);
+  } else if (warp == 1 && !(TWO && crank != 0)) {
+    // ===================== MMA issuer (2-SM mode: leader CTA only) =====================
+    const uint32_t idesc = umma_idesc_bf16(TWO ? 2 * C::BM : C::BM, BN, p.a_mn, p.b_mn);
     // K-major SW128: 8-row atoms 1024 B apart (SBO), UMMA_K=16 advances 32 B inside the row.
     // MN-major SW128: 64-element MN chunks 8192 B apart (LBO), 8-row K groups 1024 B apart
     // (SBO), UMMA_K=16 advances 16 rows = 2048 B.
@@ -186,11 +219,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int tile = w / p.splits, ks = w - tile * p.splits;
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-      mbar_wait(&tempty[acc], acc_ph ^ 1);
+      mbar_wait<2>(&tempty[acc], acc_ph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[s], ph);
+        mbar_wait<3>(&full[s], ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
@@ -199,10 +232,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int k = 0; k < C::BK / 16; ++k) {
             const uint64_t ad = umma_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024u);
             const uint64_t bd = umma_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024u);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (TWO) umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          // frees the smem slot in BOTH CTAs (each producer multicasts into the other's stage)
-          umma_commit_mc(&empty[s], (uint16_t)3);
+          // frees the smem slot in BOTH CTAs
+          if (TWO) umma_commit2_mc(&empty[s], (uint16_t)3);
+          else umma_commit_mc(&empty[s], (uint16_t)3);
         }
         __syncwarp();
         if (++s == C::STAGES) {
@@ -210,14 +245,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           ph ^= 1;
         }
       }
-      if (lane == 0) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+      if (lane == 0) {  // accumulator complete -> epilogue (of both CTAs in 2-SM mode)
+        if (TWO) umma_commit2_mc(&tfull[acc], (uint16_t)3);
+        else umma_commit(&tfull[acc]);
+      }
       __syncwarp();
       if (++acc == 2) {
         acc = 0;
         acc_ph ^= 1;
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue warps (2..9) =====================
     // Two warps per TMEM lane quadrant: warps 2..5 own the left half of the tile's columns,
     // warps 6..9 the right half (a warp may only touch lanes 32*(warp%4) .. +31).
@@ -254,7 +292,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
       };
       load_bias(0, b4, bs);
-      mbar_wait(&tfull[acc], acc_ph);
+      mbar_wait<4>(&tfull[acc], acc_ph);
       tc_fence_after();
       float run_max = -INFINITY, run_sum = 0.f;
       bool released = false;
@@ -299,7 +337,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           // last TMEM read of this accumulator: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) {
+            if (TWO) mbar_arrive_cluster(&tempty[acc], 0);  // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(&tempty[acc]);
+          }
           released = true;
         }
         if constexpr (EPI & F_LSE) {
@@ -339,11 +380,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           }
           if constexpr (EPI & F_OUT2) {
             if (p.out2) {
+              const bool deriv = p.out2_mode == 1 && p.act == MMTG_ACT_GELU_NEW;
 #pragma unroll
               for (int it = 0; it < 8; ++it)
                 if (ok[it]) {
-                  __nv_bfloat162 lo = __floats2bfloat162_rn(v[it][0], v[it][1]);
-                  __nv_bfloat162 hi = __floats2bfloat162_rn(v[it][2], v[it][3]);
+                  float w0 = v[it][0], w1 = v[it][1], w2 = v[it][2], w3 = v[it][3];
+                  if (deriv) {
+                    w0 = dgelu_new_fast(w0); w1 = dgelu_new_fast(w1);
+                    w2 = dgelu_new_fast(w2); w3 = dgelu_new_fast(w3);
+                  }
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(w0, w1);
+                  __nv_bfloat162 hi = __floats2bfloat162_rn(w2, w3);
                   uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
                   *reinterpret_cast<uint2*>(p.out2 + (row0 + it * 4) * p.ldo2 + col) = pk;
                 }
@@ -368,7 +415,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
               for (int it = 0; it < 8; ++it) {
                 const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].x));
                 const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&dsrc[it].y));
-                if (p.dact_tanh_out) {
+                if (p.dact_tanh_out == 2) {
+                  v[it][0] *= a.x; v[it][1] *= a.y; v[it][2] *= b.x; v[it][3] *= b.y;
+                } else if (p.dact_tanh_out == 1) {
                   v[it][0] *= 1.f - a.x * a.x; v[it][1] *= 1.f - a.y * a.y;
                   v[it][2] *= 1.f - b.x * b.x; v[it][3] *= 1.f - b.y * b.y;
                 } else {
@@ -519,7 +568,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         // this half-tile lies entirely beyond N: nothing was read, still release the accumulator
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if (TWO) mbar_arrive_cluster(&tempty[acc], 0);
+          else mbar_arrive(&tempty[acc]);
+        }
       }
       if (++acc == 2) {
         acc = 0;
@@ -533,7 +585,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   cluster_sync_all();  // the peer may still multicast into / arrive on this CTA until it is done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (TWO) tmem_dealloc2(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -618,13 +671,13 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
 
 void count_launch(int n = 1);
 
-template <int BN, uint32_t EPI>
+template <int BN, uint32_t EPI, bool TWO>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        cudaStream_t st) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    MMTG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>,
+    MMTG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, TWO>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
@@ -646,7 +699,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI>, tmA, tmB, p));
+  MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, TWO>, tmA, tmB, p));
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;
@@ -695,6 +748,7 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   p.colsum = a->colsum;
   p.lse_partial = a->lse_partial;
   p.dact_tanh_out = a->dact_tanh_out;
+  p.out2_mode = a->out2_mode;
   MMTG_CHECK_ARG(!(p.lse_partial && p.splits > 1), "lse_partial is incompatible with split_k");
   {
     // vector epilogue needs 16-B aligned fp32 rows / 8-B aligned bf16 rows for every operand
@@ -727,10 +781,18 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   if (p.atomic) need |= F_ATOMIC;
   if (p.lse_partial) need |= F_LSE;
   if (!p.vec4) need |= F_SCALAR;
-#define MMTG_TRY_EPI(MASK)                                         \
-  if ((need & ~(uint32_t)(MASK)) == 0) {                           \
-    if (BN == 256) return launch_gemm<256, (MASK)>(tmA, tmB, p, st); \
-    return launch_gemm<128, (MASK)>(tmA, tmB, p, st);              \
+  static const bool two_sm = []() {  // MMTG_GEMM_2SM=0 selects the 1-SM (multicast) kernel
+    const char* e = getenv("MMTG_GEMM_2SM");
+    return !(e && e[0] == '0');
+  }();
+#define MMTG_TRY_EPI(MASK)                                                        \
+  if ((need & ~(uint32_t)(MASK)) == 0) {                                          \
+    if (two_sm) {                                                                 \
+      if (BN == 256) return launch_gemm<256, (MASK), true>(tmA, tmB, p, st);      \
+      return launch_gemm<128, (MASK), true>(tmA, tmB, p, st);                     \
+    }                                                                             \
+    if (BN == 256) return launch_gemm<256, (MASK), false>(tmA, tmB, p, st);       \
+    return launch_gemm<128, (MASK), false>(tmA, tmB, p, st);                      \
   }
   MMTG_TRY_EPI(0u)
   MMTG_TRY_EPI(F_ACT | F_OUT2)

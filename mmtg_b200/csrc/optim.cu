@@ -49,7 +49,17 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, flo
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, bf16* __restrict__ p16, long long n, float lr, float b1, float b2,
-             float eps, float wd, float step_size, const float* __restrict__ normsq, float max_norm) {
+             float eps, float wd, float step_size, const float* __restrict__ normsq, float max_norm,
+             const float* __restrict__ lr_dev, const int* __restrict__ step_dev, int correct_bias) {
+  if (lr_dev) lr = lr_dev[0];
+  if (step_dev) {
+    // device-side schedule state: the launch is replayable from a CUDA graph
+    step_size = lr;
+    if (correct_bias) {
+      const float t = (float)(step_dev[0] + 1);
+      step_size = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+    }
+  }
   float clip = 1.f;
   if (normsq) clip = fminf(1.f, max_norm / (sqrtf(normsq[0]) + 1e-6f));
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
@@ -81,6 +91,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+__global__ void bump_kernel(int* c) { c[0] += 1; }
+
 }  // namespace
 }  // namespace mmtg
 
@@ -103,11 +115,13 @@ extern "C" int mmtg_grad_norm_sq(const float* grads, int64_t n, float* partial_w
 extern "C" int mmtg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                void* params_bf16, int64_t n, float lr, float beta1, float beta2,
                                float eps, float weight_decay, int32_t step, int32_t correct_bias,
-                               const float* normsq, float max_norm, void* stream) {
-  MMTG_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && step >= 1,
+                               const float* normsq, float max_norm, const float* lr_dev,
+                               int32_t* step_dev, void* stream) {
+  MMTG_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && (step >= 1 || step_dev),
                  "bad adamw args (n must be a multiple of 4)");
+  MMTG_CHECK_ARG(!(lr_dev && !step_dev), "lr_dev requires step_dev (device-side schedule state)");
   float step_size = lr;
-  if (correct_bias) {
+  if (correct_bias && !step_dev) {
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     step_size = (float)((double)lr * sqrt(bc2) / bc1);
@@ -116,8 +130,14 @@ extern "C" int mmtg_adamw_step(float* params, const float* grads, float* exp_avg
   ProfScope prof(2, 0, (double)n * 30.0, (cudaStream_t)stream);
   adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq,
                                                           (bf16*)params_bf16, n, lr, beta1, beta2, eps,
-                                                          weight_decay, step_size, normsq, max_norm);
+                                                          weight_decay, step_size, normsq, max_norm,
+                                                          lr_dev, step_dev, correct_bias);
   MMTG_LAUNCH_OK();
   count_launch();
+  if (step_dev) {
+    bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    MMTG_LAUNCH_OK();
+    count_launch();
+  }
   return 0;
 }

@@ -480,6 +480,47 @@ class MMTG(nn.Module):
         return step.scalars[0], step.scalars[1], step.logits
 
     # ------------------------------------------------------------------------------------------
+    def fused_train_step(self, batch, stage, alpha=0.2):
+        """forward + MyLoss + alpha*KL + backward in one call, WITHOUT torch.autograd in the loop:
+        the same engine entry points `forward()` / `MyLoss` / `backward()` use, driven directly
+        (restates src/train.py:188-193). Gradients are accumulated into `param.grad` (views of
+        the flat gradient buffer). No Python-side synchronisation, no autograd graph -> the call
+        is CUDA-graph capturable (mmtg_b200.graph.GraphedTrainStep). Returns (total, loss, kl)."""
+        prev = torch.is_grad_enabled()
+        torch.set_grad_enabled(False)
+        try:
+            _, _, logits = self.forward(batch)
+        finally:
+            torch.set_grad_enabled(prev)
+        step = logits._mmtg_step
+        d, dev = step.dims, logits.device
+        lib, st = _lib.lib(), C.c_void_p(_lib.stream_ptr())
+        vp = C.c_void_p
+        ratings = batch["rating"].to(device=dev, dtype=torch.int32).contiguous()
+        ce, coef = torch.empty(d.B, device=dev), torch.empty(d.B, device=dev)
+        loss = torch.empty((), device=dev)
+        _lib.check(lib.mmtg_ce_reduce(vp(logits.data_ptr()), C.c_int64(d.V), vp(step.lse_ptr), None,
+                                      vp(step.targets.data_ptr()), None, vp(ce.data_ptr()), None, d.B, d.L,
+                                      d.P, d.T, st), "mmtg_ce_reduce")
+        _lib.check(lib.mmtg_negloss(vp(ce.data_ptr()), vp(ratings.data_ptr()), int(stage), vp(loss.data_ptr()),
+                                    vp(coef.data_ptr()), d.B, st), "mmtg_negloss")
+        kl = step.scalars[1]
+        total = loss + alpha * kl
+        if getattr(self, "_unit", None) is None or self._unit.device != dev:
+            self._unit = torch.ones(1, device=dev)
+            self._alpha_buf = torch.zeros(1, device=dev)
+            self._alpha_val = None
+        if self._alpha_val != alpha:
+            self._alpha_buf.fill_(alpha)
+            self._alpha_val = alpha
+        _lib.check(lib.mmtg_ce_bwd(vp(logits.data_ptr()), C.c_int64(d.V), vp(step.lse_ptr), None,
+                                   vp(step.targets.data_ptr()), vp(coef.data_ptr()), vp(self._unit.data_ptr()),
+                                   None, vp(step.dlogits_ptr), 1, C.c_int64(d.Vp), d.B, d.L, d.P, d.T, d.V, st),
+                   "mmtg_ce_bwd")
+        _attach_grads(self)
+        _run_backward(step, self._alpha_buf)
+        return total, loss, kl
+
     def _c_model(self, d, device):
         m = Model()
         m.dims, m.off = d, self._offsets
@@ -589,26 +630,42 @@ class _MMTGFunction(torch.autograd.Function):
         gkl = None
         if g_kl is not None:
             gkl = g_kl.detach().float().contiguous()
-        # gradients are written straight into the flat gradient buffer (views = param.grad)
-        P, W16, G = mdl._flat
-        fresh = any(p.grad is None for p in mdl._named.values())
-        if fresh:
-            G.zero_()
-            for name, p in mdl._named.items():
-                off, n = mdl._layout[name]
-                p.grad = G[off:off + n].view(p.shape)
-        nstage = d.NL + 2
-        sync = mdl.grad_sync
-        for s in range(nstage):
-            rc = lib.mmtg_train_backward(C.byref(step.cm), C.byref(step.cb), wsp, C.c_int64(step.ws.numel()),
-                                         C.c_void_p(gkl.data_ptr()) if gkl is not None else None, s, s + 1, st)
-            _lib.check(rc, "mmtg_train_backward")
-            if sync is not None:
-                sync.after_stage(mdl, s, nstage)
-        if sync is not None:
-            sync.finish(mdl)
+        _attach_grads(mdl)
+        _run_backward(step, gkl)
         step.dlogits_ready = False
         return None, None
+
+
+def _attach_grads(mdl):
+    """Gradients are written straight into the flat gradient buffer: param.grad = views of it."""
+    P, W16, G = mdl._flat
+    if any(p.grad is None for p in mdl._named.values()):
+        G.zero_()
+        for name, p in mdl._named.items():
+            off, n = mdl._layout[name]
+            p.grad = G[off:off + n].view(p.shape)
+
+
+def _run_backward(step, gkl):
+    """All backward stages; after each stage the finished gradient bucket is handed to the
+    (optional) data-parallel GradSync, which all-reduces it on a side stream."""
+    mdl, d = step.model, step.dims
+    lib = _lib.lib()
+    st = C.c_void_p(_lib.stream_ptr())
+    wsp = C.c_void_p(step.ws.data_ptr())
+    nstage = d.NL + 2
+    sync = mdl.grad_sync
+    if sync is None:
+        _lib.check(lib.mmtg_train_backward(C.byref(step.cm), C.byref(step.cb), wsp, C.c_int64(step.ws.numel()),
+                                           C.c_void_p(gkl.data_ptr()) if gkl is not None else None, 0, nstage, st),
+                   "mmtg_train_backward")
+        return
+    for s in range(nstage):
+        rc = lib.mmtg_train_backward(C.byref(step.cm), C.byref(step.cb), wsp, C.c_int64(step.ws.numel()),
+                                     C.c_void_p(gkl.data_ptr()) if gkl is not None else None, s, s + 1, st)
+        _lib.check(rc, "mmtg_train_backward")
+        sync.after_stage(mdl, s, nstage)
+    sync.finish(mdl)
 
 
 def _zero_dlogits(step):

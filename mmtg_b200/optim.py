@@ -32,6 +32,9 @@ class FusedAdamW(torch.optim.Optimizer):
             self._m, self._v = torch.zeros_like(P), torch.zeros_like(P)
             self._partial = torch.empty(1024, device=P.device)
             self._normsq = torch.zeros(1, device=P.device)
+            self._lr_dev = torch.zeros(1, device=P.device)
+            self._step_dev = torch.zeros(1, device=P.device, dtype=torch.int32)
+            self._lr_host = None
         return P, W16, G
 
     @torch.no_grad()
@@ -42,6 +45,9 @@ class FusedAdamW(torch.optim.Optimizer):
         lib, st = _lib.lib(), C.c_void_p(_lib.stream_ptr())
         g = self.param_groups[0]
         self._t += 1
+        if self._lr_host != g["lr"] and not torch.cuda.is_current_stream_capturing():
+            self._lr_dev.fill_(g["lr"])  # schedule state lives on the device (graph-replayable)
+            self._lr_host = g["lr"]
         normsq = None
         if self.max_grad_norm is not None:
             _lib.check(lib.mmtg_grad_norm_sq(C.c_void_p(G.data_ptr()), C.c_int64(G.numel()),
@@ -53,8 +59,17 @@ class FusedAdamW(torch.optim.Optimizer):
                                        C.c_void_p(W16.data_ptr()), C.c_int64(P.numel()), C.c_float(g["lr"]),
                                        C.c_float(g["betas"][0]), C.c_float(g["betas"][1]), C.c_float(g["eps"]),
                                        C.c_float(g["weight_decay"]), self._t, int(g["correct_bias"]), normsq,
-                                       C.c_float(self.max_grad_norm or 0.0), st), "mmtg_adamw_step")
+                                       C.c_float(self.max_grad_norm or 0.0), C.c_void_p(self._lr_dev.data_ptr()),
+                                       C.c_void_p(self._step_dev.data_ptr()), st), "mmtg_adamw_step")
         return None
+
+    def set_lr(self, lr):
+        """Update the learning rate (host + device copy); safe between CUDA-graph replays."""
+        for g in self.param_groups:
+            g["lr"] = lr
+        self._buffers()
+        self._lr_dev.fill_(lr)
+        self._lr_host = lr
 
     def grad_norm(self):
         """Global L2 norm computed by the last step() (device tensor)."""

@@ -141,3 +141,24 @@ def test_state_dict_roundtrip_and_eval_no_grad(world, cuda):
     sd2["module.decoder.gpt2.transformer.h.0.attn.bias"] = torch.ones(1, 1, 4, 4)
     sd2["module.decoder.gpt2.transformer.h.0.attn.masked_bias"] = torch.tensor(-1e4)
     model.load_state_dict(sd2)
+
+
+def test_fused_train_step_and_graph_match_autograd_path(world, cuda):
+    """MMTG.fused_train_step (autograd-free driver) and its CUDA-graph replay produce the same
+    loss and gradients as forward() + MyLoss + backward()."""
+    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200.loss import MyLoss
+    model, sd, table = world
+    host, dev = _batch(2, 1234, cuda, ratings=np.array([5, 2]))
+    crit = MyLoss(data_config(), model_cfgs)
+    model.zero_grad(set_to_none=True)
+    hf, kl, logits = model(dev)
+    total = crit(logits, dev["targets"], dev["rating"], 3).mean() + 0.2 * kl.mean()
+    total.backward()
+    ref = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    t2, l2, k2 = model.fused_train_step(dev, 3, 0.2)
+    assert abs(t2.item() - total.item()) < 1e-5
+    for n, p in model.named_parameters():
+        err = (p.grad - ref[n]).norm().item()
+        assert err <= 2e-3 * ref[n].norm().item() + 1e-6, (n, err)  # split-K atomics reorder sums
