@@ -182,9 +182,9 @@ def main():
         opt.zero_grad()
         return total
 
-    # fixed shapes -> the whole step is replayed from one CUDA graph (launch-bound otherwise);
-    # MMTG_GRAPH=0 falls back to eager launches. Multi-GPU keeps eager launches this round.
-    use_graph = os.environ.get("MMTG_GRAPH", "1" if world == 1 else "0") == "1"
+    # fixed shapes -> the whole step (incl. the bucketed NCCL all-reduces on the side stream) is
+    # replayed from one CUDA graph (launch-bound otherwise); MMTG_GRAPH=0 = eager launches.
+    use_graph = os.environ.get("MMTG_GRAPH", "1") == "1"
     if use_graph:
         from mmtg_b200.graph import GraphedTrainStep
         step = GraphedTrainStep(model, crit, opt, resident, alpha=ALPHA, stage=STAGE, warmup=3)

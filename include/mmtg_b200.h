@@ -99,6 +99,10 @@ typedef struct mmtg_gemm_args {
 } mmtg_gemm_args;
 
 int mmtg_gemm_bf16(const mmtg_gemm_args* args, void* stream);
+/* Weight-streaming variant for generation (M <= 64 rows): same argument struct, subset of the
+ * epilogue (bias, act, residual, rowtab0 via rowidx0, rowtab1, fp32/bf16 out); A must be K-major,
+ * b_mn_major selects [K,N] (HF Conv1D) vs [N,K] (nn.Linear / tied wte) weight storage. */
+int mmtg_skinny_gemm_bf16(const mmtg_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound). Reference call sites in each comment.
@@ -132,6 +136,15 @@ int mmtg_attn_fwd(const void* qkv, const int32_t* key_mask, void* out, float* ls
 int mmtg_attn_bwd(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,
                   const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L,
                   int32_t n_head, void* stream);
+/* explicit kernel choice (tests / profiling): impl 0 = default, 1 = mma.sync tiles, 2 = tcgen05/TMEM
+ * (forward: any L; backward: L <= 256, whole head per CTA) */
+/* debugging aid: per-(block, warp) progress codes written to host-mapped memory (null = off) */
+void mmtg_attn_set_trace(int32_t* host_mapped);
+int mmtg_attn_fwd_ex(const void* qkv, const int32_t* key_mask, void* out, float* lse, int32_t B,
+                     int32_t L, int32_t n_head, int32_t impl, void* stream);
+int mmtg_attn_bwd_ex(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,
+                     const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L,
+                     int32_t n_head, int32_t impl, void* stream);
 
 /* Loss reductions: HF ForCausalLMLoss (loss/loss_utils.py:28-67) and MyLoss (src/loss.py:45-74) */
 int mmtg_lse_rows(const float* logits, int64_t ld, float* lse, int32_t M, int32_t V, void* stream);

@@ -1,0 +1,570 @@
+// tcgen05 / TMEM / TMA attention forward for the GPT-2 decoder (head_dim 64, causal + key-padding).
+// Replaces HF GPT2Attention's SDPA forward (transformers modeling_gpt2.py:54-72).
+//
+// One CTA per (128-query tile, batch row, head); 2 CTAs per SM (80 KB smem, 256 TMEM columns).
+//   warp 4 (one elected thread): TMA loads of Q / K_j / V_j straight out of the c_attn output
+//           [B*L, 3E] (one tensor map, three column offsets), issues S = Q K_j^T
+//           (tcgen05.mma 128x128x64 into TMEM) and O += P V_j (128x64x128, V consumed MN-major);
+//   warps 0-3 (128 threads = 128 TMEM lanes = 128 query rows): tcgen05.ld their S row, mask,
+//           online softmax in the exp2 domain, write P as bf16 into SWIZZLE_128B shared memory
+//           (the A operand of the second MMA), rescale O in TMEM when the running max moves,
+//           and finally normalise / store O and the row log-sum-exp.
+// Keys are processed in blocks of 128; the default sequence (L = 236) needs at most two.
+#include <stdlib.h>
+
+#include "../../include/mmtg_b200.h"
+#include "common.cuh"
+
+namespace mmtg {
+
+void count_launch(int n = 1);
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                      uint64_t ld, uint32_t box0, uint32_t box1);
+
+namespace {
+
+constexpr int TQ = 128, TK = 128, HD = 64;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnTcParams {
+  int dbg;           // bisecting aid: 1 = skip the O rescale, 2 = rescale without the TMEM store
+  volatile int* trace;  // optional host-mapped progress trace: [block][warp] = last stage reached
+  const int* kmask;  // [B, L]
+  bf16* out;         // [B*L, E]
+  float* lse;        // [B, NH, L]
+  int B, L, NH, E;
+  float scale;
+};
+
+constexpr int SMEM_Q = 0, SMEM_K = 16384, SMEM_V = 32768, SMEM_P = 49152, SMEM_BAR = 81920;
+constexpr int SMEM_TOTAL = SMEM_BAR + 64 + 4096 + 1024;  // + barriers, key mask (<= 1024 keys), slack
+
+#define ATT_TRACE(code)                                                                  \
+  do {                                                                                   \
+    if (p.trace && lane == 0) {                                                          \
+      p.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + warp] = (code);                \
+      __threadfence_system();                                                            \
+    }                                                                                    \
+  } while (0)
+
+__global__ void __launch_bounds__(160)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar_q = (uint64_t*)(smem + SMEM_BAR);
+  uint64_t* bar_kv = bar_q + 1;
+  uint64_t* bar_s = bar_q + 2;
+  uint64_t* bar_p = bar_q + 3;
+  uint64_t* bar_o = bar_q + 4;
+  uint32_t* tmem_slot = (uint32_t*)(bar_q + 5);
+  float* s_mask = (float*)(smem + SMEM_BAR + 64);  // [<= 1024] additive key mask of the whole row
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = (gridDim.x - 1) - blockIdx.x;  // heavy tiles first
+  const int bh = blockIdx.y;
+  const int b = bh / p.NH, h = bh - b * p.NH;
+  const int q0 = qt * TQ;
+  const int nkv = min(cdiv(p.L, TK), qt + 1);
+  const int row0 = b * p.L;  // first row of this batch entry in the [B*L, 3E] matrix
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  for (int k = threadIdx.x; k < nkv * TK; k += blockDim.x) {
+    const bool ok = k < p.L && (p.kmask == nullptr || p.kmask[b * p.L + k] != 0);
+    s_mask[k] = ok ? 0.f : -INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  ATT_TRACE(1);
+
+  if (warp == 4) {
+    // ===================== control warp: TMA + MMA =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm);
+      mbar_arrive_expect_tx(bar_q, TQ * HD * 2);
+      tma_load_2d(smem + SMEM_Q, &tm, bar_q, h * HD, row0 + q0);
+      const uint32_t idesc_s = umma_idesc_bf16(128, TK, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      const uint32_t aQ = smem_u32(smem + SMEM_Q), aK = smem_u32(smem + SMEM_K);
+      const uint32_t aV = smem_u32(smem + SMEM_V), aP = smem_u32(smem + SMEM_P);
+      for (int j = 0; j < nkv; ++j) {
+        ATT_TRACE(10 + 100 * j);
+        if (j > 0) mbar_wait<11>(bar_o, (uint32_t)((j - 1) & 1));  // PV(j-1) retired: K/V/P free
+        ATT_TRACE(11 + 100 * j);
+        mbar_arrive_expect_tx(bar_kv, 2 * TK * HD * 2);
+        tma_load_2d(smem + SMEM_K, &tm, bar_kv, p.E + h * HD, row0 + j * TK);
+        tma_load_2d(smem + SMEM_V, &tm, bar_kv, 2 * p.E + h * HD, row0 + j * TK);
+        if (j == 0) mbar_wait<12>(bar_q, 0);
+        ATT_TRACE(12 + 100 * j);
+        mbar_wait<13>(bar_kv, (uint32_t)(j & 1));
+        ATT_TRACE(13 + 100 * j);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tS, umma_desc_sw128(aQ + k * 32, 16, 1024), umma_desc_sw128(aK + k * 32, 16, 1024),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        ATT_TRACE(14 + 100 * j);
+        mbar_wait<14>(bar_p, (uint32_t)(j & 1));  // P written (and O rescaled) by all 128 rows
+        ATT_TRACE(15 + 100 * j);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k)
+          umma_bf16(tO, umma_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(aV + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_o);
+        ATT_TRACE(16 + 100 * j);
+      }
+    }
+    __syncwarp();
+    ATT_TRACE(90);
+  } else {
+    // ===================== softmax warps: one thread per query row =====================
+    const int r = warp * 32 + lane;  // TMEM lane == row within the tile
+    const int q = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = smem + SMEM_P + r * 128;
+    for (int j = 0; j < nkv; ++j) {
+      const float* kmask_j = s_mask + j * TK;  // key padding + sequence end, this block
+      ATT_TRACE(20 + 100 * j);
+      mbar_wait<15>(bar_s, (uint32_t)(j & 1));
+      ATT_TRACE(21 + 100 * j);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kc = c * 32 + i;
+          float s = __uint_as_float(v[i]) * sl2 + kmask_j[kc];
+          if (j * TK + kc > q) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      ATT_TRACE(22 + 100 * j);
+      const float m_new = fmaxf(m_run, mx);
+      const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+      const float corr = exp2f(m_run - m_safe);  // 0 when m_run = -inf
+      if (j > 0) {
+        // O holds the unnormalised sum up to block j-1: rescale it before PV(j) accumulates
+        mbar_wait<16>(bar_o, (uint32_t)((j - 1) & 1));
+        ATT_TRACE(23 + 100 * j);
+        tc_fence_after();
+        // tcgen05.ld/st are .sync.aligned: the whole warp takes the branch together
+        if (p.dbg != 1 && __any_sync(0xffffffffu, corr != 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + lane_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+            if (p.dbg != 2) tmem_st_32x32(tO + lane_addr + c * 32, v);
+          }
+          if (p.dbg != 2) tmem_st_wait();
+        }
+      }
+      ATT_TRACE(24 + 100 * j);
+      // pass 2: P = exp2(s - m), row sum, bf16 P into swizzled smem (K-major A operand)
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int kc = c * 32 + i;
+          float s0 = __uint_as_float(v[i]) * sl2 + kmask_j[kc];
+          float s1 = __uint_as_float(v[i + 1]) * sl2 + kmask_j[kc + 1];
+          if (j * TK + kc > q) s0 = -INFINITY;
+          if (j * TK + kc + 1 > q) s1 = -INFINITY;
+          const float e0 = exp2f(s0 - m_safe), e1 = exp2f(s1 - m_safe);
+          rs += e0 + e1;
+          __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        // 32 keys = 4 x 16-byte chunks; chunk index within the 64-key half: (c & 1) * 4 + t
+        uint8_t* half = prow + (c >> 1) * 16384;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int cc = (c & 1) * 4 + t;
+          *reinterpret_cast<uint4*>(half + ((cc ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+        }
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      ATT_TRACE(25 + 100 * j);
+    }
+    // finalize
+    mbar_wait<17>(bar_o, (uint32_t)((nkv - 1) & 1));
+    ATT_TRACE(30);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    {
+      // tcgen05.ld is .sync.aligned: every lane of the warp loads (rows beyond the sequence
+      // included); only the global stores are predicated
+      bf16* dst = p.out + ((long long)row0 + q) * p.E + h * HD;
+#pragma unroll 1
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (q < p.L) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * inv,
+                                                       __uint_as_float(v[8 * t + 2 * e + 1]) * inv);
+              w[e] = *reinterpret_cast<uint32_t*>(&x);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 32 + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      if (q < p.L && p.lse)
+        p.lse[((long long)b * p.NH + h) * p.L + q] =
+            l_run > 0.f ? (m_run + log2f(l_run)) / LOG2E : -INFINITY;
+    }
+  }
+  ATT_TRACE(40);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+  ATT_TRACE(50);
+}
+
+}  // namespace
+
+static volatile int* g_attn_trace = nullptr;
+void attn_set_trace(int* host_mapped) { g_attn_trace = host_mapped; }
+
+int attn_fwd_tc(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
+                cudaStream_t st) {
+  const int E = NH * HD;
+  CUtensorMap tm;
+  MMTG_CHECK_ARG(L <= 1024, "tcgen05 attention forward handles L <= 1024");
+  MMTG_TRY(make_tmap_bf16_2d(&tm, qkv, (uint64_t)3 * E, (uint64_t)B * L, (uint64_t)3 * E, 64, 128));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMTG_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_set = true;
+  }
+  AttnTcParams p;
+  p.kmask = kmask; p.out = out; p.lse = lse;
+  p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
+  {
+    const char* e = getenv("MMTG_ATTN_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  p.trace = g_attn_trace;
+  ProfScope prof(1, 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 4 * B * L * NH * 64, st);
+  dim3 grid(cdiv(L, TQ), B * NH);
+  attn_fwd_tc_kernel<<<grid, 160, SMEM_TOTAL, st>>>(tm, p);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace mmtg
+
+// =============================================================================================
+// tcgen05 attention BACKWARD for sequences of at most 256 positions (the default L = 236):
+// one CTA per (batch row, head) keeps Q, K, V, dO of the whole head in shared memory (8 TMA
+// boxes) and walks the causal (key block j, query block i >= j) pairs:
+//     S  = Q_i K_j^T , dP = dO_i V_j^T                  (tcgen05.mma -> TMEM, 128x128 each)
+//     P  = exp2(S*c - lse) , dS = P * (dP - delta)       (128 threads, one query row each,
+//                                                        bf16 into SWIZZLE_128B shared memory)
+//     dV_j += P^T dO_i , dK_j += dS^T Q_i , dQ_i += dS K_j   (P / dS consumed MN-major resp.
+//                                                        K-major from the SAME smem tiles)
+// dK_j / dV_j are drained after the last query block of j, dQ_i at the end; TMEM is used to the
+// last column: S 128 + dP 128 + dQ 2x64 + dK 64 + dV 64 = 512.
+// =============================================================================================
+namespace mmtg {
+namespace {
+
+struct AttnBwdTcParams {
+  const int* kmask;     // [B, L]
+  const float* lse;     // [B, NH, L]
+  const float* delta;   // [B, NH, L]
+  bf16* dqkv;           // [B*L, 3E]
+  int B, L, NH, E;
+  float scale;
+};
+
+// smem map (bytes): 8 operand tiles of 16 KB, then P and dS (32 KB each), then barriers + masks
+constexpr int BW_Q = 0, BW_K = 32768, BW_V = 65536, BW_DO = 98304, BW_P = 131072, BW_DS = 163840,
+              BW_BAR = 196608;
+constexpr int BW_SMEM_TOTAL = BW_BAR + 2048 + 1024;
+
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar_load = (uint64_t*)(smem + BW_BAR);
+  uint64_t* bar_sdp = bar_load + 1;   // S and dP of the current pair are in TMEM
+  uint64_t* bar_pds = bar_load + 2;   // P and dS of the current pair are in shared memory (128 arrivals)
+  uint64_t* bar_mma2 = bar_load + 3;  // dV/dK/dQ MMAs of the current pair have retired
+  uint64_t* bar_epi = bar_load + 4;   // dK_j/dV_j drained from TMEM (128 arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(bar_load + 5);
+  float* s_mask = (float*)(smem + BW_BAR + 64);  // [256] additive key mask
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x;
+  const int b = bh / p.NH, h = bh - b * p.NH;
+  const int nb = cdiv(p.L, 128);  // 1 or 2
+  const int row0 = b * p.L;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_pds, 128);
+    mbar_init(bar_mma2, 1);
+    mbar_init(bar_epi, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+    const bool ok = k < p.L && (p.kmask == nullptr || p.kmask[b * p.L + k] != 0);
+    s_mask[k] = ok ? 0.f : -INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDQ = tmem_base + 256, tDK = tmem_base + 384,
+                 tDV = tmem_base + 448;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      mbar_arrive_expect_tx(bar_load, (uint32_t)(nb * 4 * 16384));
+      for (int i = 0; i < nb; ++i) {
+        tma_load_2d(smem + BW_Q + i * 16384, &tm_qkv, bar_load, h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_K + i * 16384, &tm_qkv, bar_load, p.E + h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_V + i * 16384, &tm_qkv, bar_load, 2 * p.E + h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_DO + i * 16384, &tm_do, bar_load, h * 64, row0 + i * 128);
+      }
+      const uint32_t idesc_sp = umma_idesc_bf16(128, 128, 0, 0);  // S, dP: A K-major, B K-major
+      const uint32_t idesc_kv = umma_idesc_bf16(128, 64, 1, 1);   // dV, dK: A (P/dS) MN-major, B MN-major
+      const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ: A (dS) K-major, B (K) MN-major
+      const uint32_t aP = smem_u32(smem + BW_P), aDS = smem_u32(smem + BW_DS);
+      mbar_wait<21>(bar_load, 0);
+      int pair = 0;
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t aK = smem_u32(smem + BW_K + j * 16384), aV = smem_u32(smem + BW_V + j * 16384);
+        for (int i = j; i < nb; ++i, ++pair) {
+          const uint32_t aQ = smem_u32(smem + BW_Q + i * 16384), aDO = smem_u32(smem + BW_DO + i * 16384);
+          // S/dP TMEM is free once the softmax threads have consumed the previous pair (bar_pds
+          // of pair-1, waited below before the second-stage MMAs of that pair were issued).
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tS, umma_desc_sw128(aQ + k * 32, 16, 1024), umma_desc_sw128(aK + k * 32, 16, 1024),
+                      idesc_sp, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tDP, umma_desc_sw128(aDO + k * 32, 16, 1024), umma_desc_sw128(aV + k * 32, 16, 1024),
+                      idesc_sp, k > 0 ? 1u : 0u);
+          umma_commit(bar_sdp);
+          if (i == j && j > 0) mbar_wait<22>(bar_epi, (uint32_t)((j - 1) & 1));  // dK/dV of j-1 drained
+          mbar_wait<23>(bar_pds, (uint32_t)(pair & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // reduction over the 128 query rows of block i
+            const uint64_t dP_ = umma_desc_sw128(aP + k * 2048, 16384, 1024);
+            const uint64_t dDS = umma_desc_sw128(aDS + k * 2048, 16384, 1024);
+            umma_bf16(tDV, dP_, umma_desc_sw128(aDO + k * 2048, 8192, 1024), idesc_kv, (i > j || k > 0) ? 1u : 0u);
+            umma_bf16(tDK, dDS, umma_desc_sw128(aQ + k * 2048, 8192, 1024), idesc_kv, (i > j || k > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // reduction over the 128 keys of block j
+            umma_bf16(tDQ + i * 64, umma_desc_sw128(aDS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      umma_desc_sw128(aK + k * 2048, 8192, 1024), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_mma2);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    uint8_t* prow = smem + BW_P + r * 128;
+    uint8_t* dsrow = smem + BW_DS + r * 128;
+    int pair = 0;
+    for (int j = 0; j < nb; ++j) {
+      for (int i = j; i < nb; ++i, ++pair) {
+        const int q = i * 128 + r;
+        const long long so = ((long long)b * p.NH + h) * p.L + q;
+        float lse2 = INFINITY, dl = 0.f;  // +inf -> P = 0 for rows beyond the sequence
+        if (q < p.L) {
+          const float lv = p.lse[so];
+          lse2 = lv == -INFINITY ? INFINITY : lv * LOG2E;
+          dl = p.delta[so];
+        }
+        mbar_wait<25>(bar_sdp, (uint32_t)(pair & 1));
+        if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(tS + lane_addr + c * 32, sv);
+          tmem_ld_32x32(tDP + lane_addr + c * 32, dv);
+          tmem_ld_wait();
+          uint32_t pp[16], pd[16];
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            float pe[2], de[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int kc = c * 32 + t + e;
+              const int key = j * 128 + kc;
+              float pv = 0.f;
+              if (key <= q && s_mask[key] == 0.f) pv = exp2f(__uint_as_float(sv[t + e]) * sl2 - lse2);
+              pe[e] = pv;
+              de[e] = pv * (__uint_as_float(dv[t + e]) - dl);
+            }
+            __nv_bfloat162 a = __floats2bfloat162_rn(pe[0], pe[1]), d2 = __floats2bfloat162_rn(de[0], de[1]);
+            pp[t >> 1] = *reinterpret_cast<uint32_t*>(&a);
+            pd[t >> 1] = *reinterpret_cast<uint32_t*>(&d2);
+          }
+          const int hoff = (c >> 1) * 16384;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int cc = (c & 1) * 4 + t;
+            const int off = hoff + ((cc ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[4 * t], pp[4 * t + 1], pp[4 * t + 2], pp[4 * t + 3]);
+            *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(pd[4 * t], pd[4 * t + 1], pd[4 * t + 2], pd[4 * t + 3]);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+      }
+      // ---- drain dK_j / dV_j: TMEM lane r = key j*128 + r ----
+      mbar_wait<27>(bar_mma2, (uint32_t)((pair - 1) & 1));
+      tc_fence_after();
+      {
+        const int key = j * 128 + r;
+        bf16* dst = p.dqkv + ((long long)row0 + key) * 3 * p.E + h * 64;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {  // c 0,1: dK columns 0..63; c 2,3: dV columns 0..63
+          uint32_t v[32];
+          tmem_ld_32x32((c < 2 ? tDK : tDV) + lane_addr + (c & 1) * 32, v);
+          tmem_ld_wait();
+          if (key < p.L) {
+            const float sc = c < 2 ? p.scale : 1.f;
+            bf16* d = dst + (c < 2 ? p.E : 2 * p.E) + (c & 1) * 32;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * sc,
+                                                         __uint_as_float(v[8 * t + 2 * e + 1]) * sc);
+                w[e] = *reinterpret_cast<uint32_t*>(&x);
+              }
+              *reinterpret_cast<uint4*>(d + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_epi);
+    }
+    // ---- drain dQ_i (all second-stage MMAs retired: bar_mma2 of the last pair was waited above) ----
+    for (int i = 0; i < nb; ++i) {
+      const int q = i * 128 + r;
+      bf16* dst = p.dqkv + ((long long)row0 + q) * 3 * p.E + h * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tDQ + i * 64 + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (q < p.L) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * p.scale,
+                                                       __uint_as_float(v[8 * t + 2 * e + 1]) * p.scale);
+              w[e] = *reinterpret_cast<uint32_t*>(&x);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 32 + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// dqkv for L <= 256; `delta` must already hold rowsum(dO * O) (attn_delta_kernel).
+int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float* lse, const float* delta,
+                bf16* dqkv, int B, int L, int NH, cudaStream_t st) {
+  MMTG_CHECK_ARG(L <= 256, "tcgen05 attention backward handles L <= 256");
+  const int E = NH * 64;
+  CUtensorMap tm_qkv, tm_do;
+  MMTG_TRY(make_tmap_bf16_2d(&tm_qkv, qkv, (uint64_t)3 * E, (uint64_t)B * L, (uint64_t)3 * E, 64, 128));
+  MMTG_TRY(make_tmap_bf16_2d(&tm_do, dout, (uint64_t)E, (uint64_t)B * L, (uint64_t)E, 64, 128));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_TOTAL));
+    attr_set = true;
+  }
+  AttnBwdTcParams p;
+  p.kmask = kmask; p.lse = lse; p.delta = delta; p.dqkv = dqkv;
+  p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
+  attn_bwd_tc_kernel<<<B * NH, 160, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace mmtg
+
+// debugging aid: progress trace into host-mapped (pinned) memory, readable while a kernel hangs
+extern "C" void mmtg_attn_set_trace(int32_t* host_mapped) { mmtg::attn_set_trace(host_mapped); }

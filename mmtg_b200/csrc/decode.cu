@@ -19,8 +19,15 @@
 namespace mmtg {
 
 void count_launch(int n = 1);
+int skinny_gemm(const mmtg_gemm_args* a, cudaStream_t st);
 
 namespace {
+
+// decode GEMMs: weight-streaming skinny kernel for <= 64 rows, tcgen05 kernel otherwise
+inline int decode_gemm(const mmtg_gemm_args* a, void* stream) {
+  if (a->M <= 64) return skinny_gemm(a, (cudaStream_t)stream);
+  return mmtg_gemm_bf16(a, stream);
+}
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -455,12 +462,12 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
   {
     mmtg_gemm_args a = gemm(w.emb16, Dw, W + o.proj1_w, Dw, false, He, Dw);
     a.out = w.p1; a.ldo = He; a.out_dtype = MMTG_BF16; a.bias = P + o.proj1_b; a.act = MMTG_ACT_TANH;
-    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    MMTG_TRY(decode_gemm(&a, stream));
     a = gemm(w.p1, He, W + o.proj2_w, He, false, E, He);
     a.out = w.h; a.ldo = E; a.out_dtype = MMTG_F32; a.bias = P + o.proj2_b;
     a.rowtab0 = P + o.wpe; a.ldt0 = E; a.rowidx0 = w.posidx;
     a.rowtab1 = P + o.wte; a.ldt1 = E; a.rowidx1 = w.types;
-    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    MMTG_TRY(decode_gemm(&a, stream));
   }
   const size_t layer_cache = (size_t)B * d.NH * Lmax * 64;
   const int att_smem = 4 * Lmax * 4;
@@ -469,7 +476,7 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
     MMTG_TRY(layernorm_fwd(w.h, P + lo.ln1_w, P + lo.ln1_b, w.x16, nullptr, nullptr, nullptr, B, E, eps, st));
     mmtg_gemm_args a = gemm(w.x16, E, W + lo.attn_w, 3 * E, true, 3 * E, E);
     a.out = w.qkv16; a.ldo = 3 * E; a.out_dtype = MMTG_BF16; a.bias = P + lo.attn_b;
-    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    MMTG_TRY(decode_gemm(&a, stream));
     decode_attn_kernel<<<cdiv(B * d.NH, 4), 128, att_smem, st>>>(
         w.qkv16, w.kcache + l * layer_cache, w.vcache + l * layer_cache, w.keymask, j_ptr, w.att16, B, d.NH,
         d.P, Lmax);
@@ -477,19 +484,19 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
     count_launch();
     a = gemm(w.att16, E, W + lo.proj_w, E, true, E, E);
     a.out = w.h2; a.ldo = E; a.out_dtype = MMTG_F32; a.bias = P + lo.proj_b; a.residual = w.h; a.ldr = E;
-    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    MMTG_TRY(decode_gemm(&a, stream));
     MMTG_TRY(layernorm_fwd(w.h2, P + lo.ln2_w, P + lo.ln2_b, w.x16, nullptr, nullptr, nullptr, B, E, eps, st));
     a = gemm(w.x16, E, W + lo.fc_w, 4 * E, true, 4 * E, E);
     a.out = w.a16; a.ldo = 4 * E; a.out_dtype = MMTG_BF16; a.bias = P + lo.fc_b; a.act = MMTG_ACT_GELU_NEW;
-    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    MMTG_TRY(decode_gemm(&a, stream));
     a = gemm(w.a16, 4 * E, W + lo.proj2_w, E, true, E, 4 * E);
     a.out = w.h; a.ldo = E; a.out_dtype = MMTG_F32; a.bias = P + lo.proj2_b; a.residual = w.h2; a.ldr = E;
-    MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+    MMTG_TRY(decode_gemm(&a, stream));
   }
   MMTG_TRY(layernorm_fwd(w.h, P + o.lnf_w, P + o.lnf_b, w.x16, nullptr, nullptr, nullptr, B, E, eps, st));
   mmtg_gemm_args a = gemm(w.x16, E, W + o.wte, E, false, d.V, E);
   a.out = logits; a.ldo = d.V; a.out_dtype = MMTG_F32;
-  MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+  MMTG_TRY(decode_gemm(&a, stream));
   return 0;
 }
 

@@ -1,12 +1,17 @@
 """CUDA-graphed training step for fixed batch shapes.
 
 The train step issues ~380 kernel launches; on a busy host the Python/driver launch path, not the
-GPU, sets the step time. `GraphedTrainStep` captures forward + MyLoss + alpha*KL + backward
-(+ gradient all-reduce) + clip + AdamW once (through `MMTG.fused_train_step`, the autograd-free
-driver of the same engine entry points) and replays it; inputs are copied into static device
-buffers before each replay, learning-rate / step-count state lives on the device
-(mmtg_b200.optim.FusedAdamW). Shapes must not change between calls (curriculum-filtered batches
-of another size need their own instance).
+GPU, sets the step time. `GraphedTrainStep` captures the step once and replays it. It drives the
+engine through `MMTG.fused_forward_loss` / `backward_stages` (the autograd-free drivers of the
+same C-ABI entry points); inputs are copied into static device buffers before each replay and
+learning-rate / step-count state lives on the device (mmtg_b200.optim.FusedAdamW).
+
+Single GPU: one graph (forward + MyLoss + alpha*KL + backward + clip + AdamW).
+Data parallel (`model.grad_sync` set): one graph for forward+loss, one per backward stage and one
+for the optimizer, sharing a memory pool; the bucketed NCCL all-reduces stay EAGER and are issued
+between the stage replays on GradSync's side stream (no collectives inside a capture).
+Shapes must not change between calls (a curriculum-filtered batch of another size needs its own
+instance).
 """
 from __future__ import annotations
 
@@ -18,6 +23,7 @@ class GraphedTrainStep:
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.alpha, self.stage = alpha, stage
         self.static = {k: v.detach().clone() for k, v in example_batch.items()}
+        self.sync = model.grad_sync
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -25,12 +31,29 @@ class GraphedTrainStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.total = self._eager()
+        if self.sync is None:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.total = self._eager()
+            return
+        # segmented capture: collectives are issued eagerly between the segments
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            self.step, self.total, _, _ = model.fused_forward_loss(self.static, stage, alpha)
+        pool = self.g_fwd.pool()
+        self.nstage = self.step.dims.NL + 2
+        self.g_stage = []
+        for s in range(self.nstage):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                model.backward_stages(self.step, s, s + 1)
+            self.g_stage.append(g)
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt, pool=pool):
+            optimizer.step()
+            optimizer.zero_grad()
 
     def _eager(self):
-        # engine-driven step (no torch.autograd inside the capture): same kernels, same C-ABI
         total, _loss, _kl = self.model.fused_train_step(self.static, self.stage, self.alpha)
         self.optimizer.step()
         self.optimizer.zero_grad()
@@ -43,5 +66,13 @@ class GraphedTrainStep:
             src = batch[k]
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
-        self.graph.replay()
+        if self.sync is None:
+            self.graph.replay()
+            return self.total
+        self.g_fwd.replay()
+        for s, g in enumerate(self.g_stage):
+            g.replay()
+            self.sync.after_stage(self.model, s, self.nstage)
+        self.sync.finish(self.model)
+        self.g_opt.replay()
         return self.total

@@ -480,12 +480,10 @@ class MMTG(nn.Module):
         return step.scalars[0], step.scalars[1], step.logits
 
     # ------------------------------------------------------------------------------------------
-    def fused_train_step(self, batch, stage, alpha=0.2):
-        """forward + MyLoss + alpha*KL + backward in one call, WITHOUT torch.autograd in the loop:
-        the same engine entry points `forward()` / `MyLoss` / `backward()` use, driven directly
-        (restates src/train.py:188-193). Gradients are accumulated into `param.grad` (views of
-        the flat gradient buffer). No Python-side synchronisation, no autograd graph -> the call
-        is CUDA-graph capturable (mmtg_b200.graph.GraphedTrainStep). Returns (total, loss, kl)."""
+    def fused_forward_loss(self, batch, stage, alpha=0.2):
+        """forward + MyLoss + the bf16 dlogits operand, WITHOUT torch.autograd: the same engine
+        entry points `forward()` / `MyLoss` use, driven directly (restates src/train.py:188-192).
+        Returns (step, total, loss, kl); `backward_stages(step, ...)` completes the step."""
         prev = torch.is_grad_enabled()
         torch.set_grad_enabled(False)
         try:
@@ -517,7 +515,24 @@ class MMTG(nn.Module):
                                    vp(step.targets.data_ptr()), vp(coef.data_ptr()), vp(self._unit.data_ptr()),
                                    None, vp(step.dlogits_ptr), 1, C.c_int64(d.Vp), d.B, d.L, d.P, d.T, d.V, st),
                    "mmtg_ce_bwd")
+        step.keep = (ratings, ce, coef)
         _attach_grads(self)
+        return step, total, loss, kl
+
+    def backward_stages(self, step, s0=0, s1=None):
+        """Run backward stages [s0, s1) of `step` (0 = lm_head, 1..NL = blocks NL-1..0, NL+1 =
+        embeddings/encoder) with d(total)/d(kl) = alpha; gradients accumulate into param.grad."""
+        d = step.dims
+        s1 = d.NL + 2 if s1 is None else s1
+        _lib.check(_lib.lib().mmtg_train_backward(C.byref(step.cm), C.byref(step.cb), C.c_void_p(step.ws.data_ptr()),
+                                                  C.c_int64(step.ws.numel()), C.c_void_p(self._alpha_buf.data_ptr()),
+                                                  s0, s1, C.c_void_p(_lib.stream_ptr())), "mmtg_train_backward")
+
+    def fused_train_step(self, batch, stage, alpha=0.2):
+        """fused_forward_loss + all backward stages (+ bucketed gradient all-reduce when
+        `grad_sync` is set). No Python-side synchronisation and no autograd graph, so the call is
+        CUDA-graph capturable (mmtg_b200.graph.GraphedTrainStep). Returns (total, loss, kl)."""
+        step, total, loss, kl = self.fused_forward_loss(batch, stage, alpha)
         _run_backward(step, self._alpha_buf)
         return total, loss, kl
 

@@ -18,7 +18,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          a_mn_major: bool = False, b_mn_major: bool = False, bias=None, act: int = ACT_NONE,
          out2=None, residual=None, dgelu_src=None, rowtab0=None, rowidx0=None, rowmod0: int = 0,
          rowtab1=None, rowidx1=None, colsum=None, lse_partial=None, accumulate: bool = False,
-         split_k: int = 1, block_n: int = 0) -> torch.Tensor:
+         split_k: int = 1, block_n: int = 0, skinny: bool = False) -> torch.Tensor:
     """out = epilogue(A · Bᵀ) on the tcgen05 GEMM (see include/mmtg_b200.h: mmtg_gemm_bf16)."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert out.dtype in (torch.float32, torch.bfloat16)
@@ -60,7 +60,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     if lse_partial is not None:
         assert lse_partial.dtype == torch.float32
         a.lse_partial = lse_partial.data_ptr()
-    _lib.check(_lib.lib().mmtg_gemm_bf16(C.byref(a), C.c_void_p(_lib.stream_ptr())), "mmtg_gemm_bf16")
+    fn = _lib.lib().mmtg_skinny_gemm_bf16 if skinny else _lib.lib().mmtg_gemm_bf16
+    _lib.check(fn(C.byref(a), C.c_void_p(_lib.stream_ptr())), "mmtg_gemm_bf16")
     return out
 
 
@@ -96,17 +97,19 @@ def colsum(x, out, copy16=None):
                                       _st()), "mmtg_colsum")
 
 
-def attn_fwd(qkv, mask, B, L, NH):
+def attn_fwd(qkv, mask, B, L, NH, impl=0):
+    """impl: 0 default, 1 mma.sync tiles, 2 tcgen05/TMEM."""
     E = NH * 64
     out = torch.empty(B * L, E, device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(B, NH, L, device=qkv.device)
-    _lib.check(_lib.lib().mmtg_attn_fwd(_p(qkv), _p(mask), _p(out), _p(lse), B, L, NH, _st()), "mmtg_attn_fwd")
+    _lib.check(_lib.lib().mmtg_attn_fwd_ex(_p(qkv), _p(mask), _p(out), _p(lse), B, L, NH, impl, _st()),
+               "mmtg_attn_fwd")
     return out, lse
 
 
-def attn_bwd(qkv, mask, out, dout, lse, B, L, NH):
-    dqkv = torch.empty_like(qkv)
+def attn_bwd(qkv, mask, out, dout, lse, B, L, NH, impl=0):
+    dqkv = torch.full_like(qkv, float("nan"))
     delta = torch.empty(B, NH, L, device=qkv.device)
-    _lib.check(_lib.lib().mmtg_attn_bwd(_p(qkv), _p(mask), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, L,
-                                        NH, _st()), "mmtg_attn_bwd")
+    _lib.check(_lib.lib().mmtg_attn_bwd_ex(_p(qkv), _p(mask), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B,
+                                           L, NH, impl, _st()), "mmtg_attn_bwd")
     return dqkv

@@ -115,3 +115,36 @@ def test_gemm_lmhead_odd_pitch_and_lse(cuda):
         w = torch.where(part[..., 1] > 0, part[..., 1] * torch.exp(part[..., 0] - mx), torch.zeros_like(mx))
         lse = mx + torch.log(w.sum(0))
         assert torch.allclose(lse, torch.logsumexp(ref, -1), atol=1e-3, rtol=1e-5)
+
+
+@pytest.mark.parametrize("M", [1, 17, 64])
+@pytest.mark.parametrize("N,K,w_kn", [(768, 768, True), (2304, 768, True), (768, 3072, True), (512, 2048, False),
+                                      (13317, 768, False), (768, 512, False)])
+def test_skinny_decode_gemm(cuda, M, N, K, w_kn):
+    """Weight-streaming decode GEMM vs fp32 reference, both weight layouts, fused epilogues."""
+    from mmtg_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g, device=cuda).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device=cuda) * 0.05).to(torch.bfloat16)  # logical [N, K]
+    Ws = W.t().contiguous() if w_kn else W
+    if w_kn and N % 8:
+        pytest.skip("[K,N] storage needs N % 8 == 0")
+    bias = torch.randn(N, generator=g, device=cuda)
+    res = torch.randn(M, N, generator=g, device=cuda)
+    base = x.float() @ W.float().t() + bias
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm(x, Ws, out, M=M, N=N, K=K, b_mn_major=w_kn, bias=bias, residual=res, skinny=True)
+    tol = 3e-3 * math.sqrt(K / 64)
+    assert (out - (base + res)).abs().max().item() <= tol
+    out16 = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(x, Ws, out16, M=M, N=N, K=K, b_mn_major=w_kn, bias=bias, act=ops.ACT_GELU_NEW, skinny=True)
+    ref = torch.nn.functional.gelu(base, approximate="tanh")
+    assert torch.allclose(out16.float(), ref, atol=tol, rtol=8e-3)
+    if N % 4 == 0:
+        tab0 = torch.randn(300, N, generator=g, device=cuda)
+        tab1 = torch.randn(16, N, generator=g, device=cuda)
+        i0 = torch.randint(0, 300, (M,), generator=g, device=cuda, dtype=torch.int32)
+        i1 = torch.randint(0, 16, (M,), generator=g, device=cuda, dtype=torch.int32)
+        ops.gemm(x, Ws, out, M=M, N=N, K=K, b_mn_major=w_kn, bias=bias, rowtab0=tab0, rowidx0=i0, rowtab1=tab1,
+                 rowidx1=i1, skinny=True)
+        assert (out - (base + tab0[i0.long()] + tab1[i1.long()])).abs().max().item() <= tol

@@ -162,3 +162,50 @@ def test_fused_train_step_and_graph_match_autograd_path(world, cuda):
     for n, p in model.named_parameters():
         err = (p.grad - ref[n]).norm().item()
         assert err <= 2e-3 * ref[n].norm().item() + 1e-6, (n, err)  # split-K atomics reorder sums
+
+
+@pytest.mark.parametrize("max_sent_length", [40])
+def test_extended_lyrics_length_forward_backward(cuda, max_sent_length):
+    """BASELINE.json configs[4]: extended lyrics length (L = 15 + 10*(msl+2) + 1 = 436) — forward
+    and gradient parity vs the oracle with a 2-layer decoder (keeps the CPU oracle fast)."""
+    from mmtg_b200 import synth
+    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200.loss import MyLoss
+    from mmtg_b200.model import MMTG
+    from oracle import mmtg_oracle as O
+    dc = data_config(max_sent_length=max_sent_length)
+    g2 = {"n_layer": 2}
+    table = synth.make_token_table()
+    sd = synth.make_state_dict(1, gpt2_cfg=g2)
+    model = MMTG(model_cfgs, dc, 13317, train_flag=True, token_table=table, gpt2_config=g2)
+    model.load_state_dict(sd)
+    model.to(cuda)
+    host = synth.batch_to_torch(synth.make_batch(2, seed=11, data_config=dc, ratings=np.array([1, 5])))
+    dev = {k: v.to(cuda) for k, v in host.items()}
+    assert host["targets"].shape[1] == 10 * (max_sent_length + 2) + 1
+    crit = MyLoss(dc, model_cfgs)
+    hf, kl, logits = model(dev)
+    total = crit(logits, dev["targets"], dev["rating"], 3).mean() + 0.2 * kl.mean()
+    total.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "decoder.gpt2.lm_head.weight"}
+    params["decoder.gpt2.lm_head.weight"] = params["decoder.gpt2.transformer.wte.weight"]
+    ctx, okl = O.fused_context(params, host)
+    t_emb, i_emb = O.decoder_embed(torch.from_numpy(table), ctx, host["topic_ids"], host["targets"], 2 * (max_sent_length + 2))
+    emb = torch.cat([t_emb, i_emb], 1)
+    types = torch.cat([host["tpw_type_ids"], host["type_ids"]], 1)
+    mask = torch.cat([host["tpw_attention_mask"], host["attention_mask"]], 1)
+    h1 = torch.tanh(emb @ params["decoder.projector_layer1.weight"].t() + params["decoder.projector_layer1.bias"])
+    x = h1 @ params["decoder.projector_layer2.weight"].t() + params["decoder.projector_layer2.bias"]
+    ologits = O.gpt2_forward(params, x, types, mask, n_layer=2)
+    ototal = O.my_loss(ologits, host["targets"], host["rating"], 3).mean() + 0.2 * okl
+    ototal.backward()
+    d = (logits.detach().cpu() - ologits.detach()).abs()
+    assert d.max().item() <= 0.05 and d.mean().item() <= 0.01
+    assert abs(total.item() - ototal.item()) <= 3e-3 * max(1.0, abs(ototal.item()))
+    bad = []
+    for n, p in model.named_parameters():
+        ref = params[n].grad
+        err = (p.grad.detach().cpu() - ref).norm().item()
+        if err > 5e-2 * ref.norm().item() + 1e-4:
+            bad.append((n, err, ref.norm().item()))
+    assert not bad, bad
