@@ -243,11 +243,12 @@ int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_workspace, 
                      int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
                      float* logits, void* stream);
 /* ban_specials: set ids 1, 2, 100, 102 to -inf (src/generate.py:133-136).
+ * seed_dev (optional, device): overrides `seed`, so a captured launch can be re-seeded.
  * dbg_probs (optional): [B, 1024, 2] (kept token id, probability) of the filtered distribution */
 int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_ld, int32_t* j_ptr,
                      int32_t B, int32_t V, int32_t sent_len, float temperature, int32_t top_k,
-                     float top_p, float rep_penalty, uint64_t seed, int32_t ban_specials,
-                     float* dbg_probs, void* stream);
+                     float top_p, float rep_penalty, uint64_t seed, const uint64_t* seed_dev,
+                     int32_t ban_specials, float* dbg_probs, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer step over the flat buffers: clip_grad_norm_ (src/train.py:194) and

@@ -302,7 +302,7 @@ int attn_fwd_tc(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B,
 // one CTA per (batch row, head) keeps Q, K, V, dO of the whole head in shared memory (8 TMA
 // boxes) and walks the causal (key block j, query block i >= j) pairs:
 //     S  = Q_i K_j^T , dP = dO_i V_j^T                  (tcgen05.mma -> TMEM, 128x128 each)
-//     P  = exp2(S*c - lse) , dS = P * (dP - delta)       (128 threads, one query row each,
+//     P  = exp2(S*c - lse) , dS = P * (dP - delta)       (256 threads, two per query row,
 //                                                        bf16 into SWIZZLE_128B shared memory)
 //     dV_j += P^T dO_i , dK_j += dS^T Q_i , dQ_i += dS K_j   (P / dS consumed MN-major resp.
 //                                                        K-major from the SAME smem tiles)
@@ -326,7 +326,7 @@ constexpr int BW_Q = 0, BW_K = 32768, BW_V = 65536, BW_DO = 98304, BW_P = 131072
               BW_BAR = 196608;
 constexpr int BW_SMEM_TOTAL = BW_BAR + 2048 + 1024;
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(288, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const AttnBwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -348,12 +348,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   if (threadIdx.x == 0) {
     mbar_init(bar_load, 1);
     mbar_init(bar_sdp, 1);
-    mbar_init(bar_pds, 128);
+    mbar_init(bar_pds, 256);
     mbar_init(bar_mma2, 1);
-    mbar_init(bar_epi, 128);
+    mbar_init(bar_epi, 256);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -368,7 +368,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDQ = tmem_base + 256, tDK = tmem_base + 384,
                  tDV = tmem_base + 448;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_do);
@@ -421,8 +421,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     __syncwarp();
   } else {
-    const int r = warp * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    // two threads per query row: warps 0-3 take key columns 0..63, warps 4-7 columns 64..127
+    // (a warp may only touch TMEM lanes 32*(warp%4) .. +31, any columns)
+    const int r = (warp & 3) * 32 + lane;
+    const int ch = warp >> 2;  // column half
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     uint8_t* prow = smem + BW_P + r * 128;
     uint8_t* dsrow = smem + BW_DS + r * 128;
@@ -441,7 +444,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
           uint32_t sv[32], dv[32];
           tmem_ld_32x32(tS + lane_addr + c * 32, sv);
           tmem_ld_32x32(tDP + lane_addr + c * 32, dv);
@@ -483,7 +486,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const int key = j * 128 + r;
         bf16* dst = p.dqkv + ((long long)row0 + key) * 3 * p.E + h * 64;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {  // c 0,1: dK columns 0..63; c 2,3: dV columns 0..63
+        for (int c = 2 * ch; c < 2 * ch + 2; ++c) {  // c 0,1 (half 0): dK; c 2,3 (half 1): dV
           uint32_t v[32];
           tmem_ld_32x32((c < 2 ? tDK : tDV) + lane_addr + (c & 1) * 32, v);
           tmem_ld_wait();
@@ -511,8 +514,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int i = 0; i < nb; ++i) {
       const int q = i * 128 + r;
       bf16* dst = p.dqkv + ((long long)row0 + q) * 3 * p.E + h * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = ch;  // each half drains 32 of the 64 dQ columns
         uint32_t v[32];
         tmem_ld_32x32(tDQ + i * 64 + lane_addr + c * 32, v);
         tmem_ld_wait();
@@ -534,7 +537,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -558,7 +561,7 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float
   AttnBwdTcParams p;
   p.kmask = kmask; p.lse = lse; p.delta = delta; p.dqkv = dqkv;
   p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
-  attn_bwd_tc_kernel<<<B * NH, 160, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
+  attn_bwd_tc_kernel<<<B * NH, 288, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;

@@ -107,27 +107,27 @@ decode_prep_kernel(const int* __restrict__ gen, int gen_ld, const int* __restric
   }
 }
 
-// One warp per (row, head): append this step's K/V to the cache, then attend over keys 0..pos
-// with the key-padding mask. Scores live in shared memory (any context length).
+// One 128-thread block per (row, head): append this step's K/V to the cache, then attend over
+// keys 0..pos with the key-padding mask. The keys are split across the 4 warps (each lane scores
+// whole keys: one 128-byte row per lane), partial (max, sum, output) merged in shared memory.
 __global__ void __launch_bounds__(128)
 decode_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc,
                    const int* __restrict__ keymask, const int* __restrict__ j_ptr,
                    bf16* __restrict__ out, int B, int NH, int P, int Lmax) {
-  extern __shared__ float s_scores[];  // [4 warps][Lmax]
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (w >= B * NH) return;
-  const int b = w / NH, h = w - b * NH, l = lane_id();
+  extern __shared__ float s_scores[];  // [Lmax] scores, then [4][66] partials
+  float* s_part = s_scores + Lmax;
+  const int w = blockIdx.x;
+  const int b = w / NH, h = w - b * NH;
+  const int warp = threadIdx.x >> 5, l = lane_id();
   const int pos = P + *j_ptr;
   const int E = NH * 64;
-  float* sc = s_scores + (threadIdx.x >> 5) * Lmax;
   const bf16* row = qkv + (long long)b * 3 * E + h * 64;
   bf16* kbase = kc + ((long long)b * NH + h) * Lmax * 64;
   bf16* vbase = vc + ((long long)b * NH + h) * Lmax * 64;
-  // append
-  reinterpret_cast<uint32_t*>(kbase + (long long)pos * 64)[l] = reinterpret_cast<const uint32_t*>(row + E)[l];
-  reinterpret_cast<uint32_t*>(vbase + (long long)pos * 64)[l] = reinterpret_cast<const uint32_t*>(row + 2 * E)[l];
-  __syncwarp();
-  // q in registers (all 64 dims per lane, as fp32)
+  if (warp == 0) {  // append (visible to the other warps after the barrier below)
+    reinterpret_cast<uint32_t*>(kbase + (long long)pos * 64)[l] = reinterpret_cast<const uint32_t*>(row + E)[l];
+    reinterpret_cast<uint32_t*>(vbase + (long long)pos * 64)[l] = reinterpret_cast<const uint32_t*>(row + 2 * E)[l];
+  }
   float q[64];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -140,8 +140,10 @@ decode_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __
       q[i * 8 + 2 * e + 1] = f.y;
     }
   }
+  __syncthreads();
+  // scores: thread t handles keys t, t+128, ...
   float mx = -INFINITY;
-  for (int key = l; key <= pos; key += 32) {
+  for (int key = threadIdx.x; key <= pos; key += 128) {
     float d = -INFINITY;
     if (keymask[b * Lmax + key] != 0) {
       const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)key * 64);
@@ -158,23 +160,31 @@ decode_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __
       }
       d *= 0.125f;
     }
-    sc[key] = d;
+    s_scores[key] = d;
     mx = fmaxf(mx, d);
   }
   mx = warp_max(mx);
+  if (l == 0) s_part[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_part[0], s_part[1]), fmaxf(s_part[2], s_part[3]));
   if (mx == -INFINITY) mx = 0.f;
+  __syncthreads();
   float sum = 0.f;
-  for (int key = l; key <= pos; key += 32) {
-    const float e = __expf(sc[key] - mx);
-    sc[key] = e;
+  for (int key = threadIdx.x; key <= pos; key += 128) {
+    const float e = __expf(s_scores[key] - mx);
+    s_scores[key] = e;
     sum += e;
   }
   sum = warp_sum(sum);
-  __syncwarp();
+  if (l == 0) s_part[warp] = sum;
+  __syncthreads();
+  sum = s_part[0] + s_part[1] + s_part[2] + s_part[3];
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  __syncthreads();
+  // output: warp w sums keys w, w+4, ...; lane l owns dims 2l, 2l+1
   float2 acc = make_float2(0.f, 0.f);
-  for (int key = 0; key <= pos; ++key) {
-    const float pj = sc[key];
+  for (int key = warp; key <= pos; key += 4) {
+    const float pj = s_scores[key];
     if (pj != 0.f) {
       const float2 v = __bfloat1622float2(
           reinterpret_cast<const __nv_bfloat162*>(vbase + (long long)key * 64)[l]);
@@ -182,8 +192,18 @@ decode_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __
       acc.y += pj * v.y;
     }
   }
-  reinterpret_cast<__nv_bfloat162*>(out + (long long)b * E + h * 64)[l] =
-      __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
+  s_part[4 + warp * 64 + 2 * l] = acc.x;
+  s_part[4 + warp * 64 + 2 * l + 1] = acc.y;
+  __syncthreads();
+  if (warp == 0) {
+    float ox = 0.f, oy = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 4; ++ww) {
+      ox += s_part[4 + ww * 64 + 2 * l];
+      oy += s_part[4 + ww * 64 + 2 * l + 1];
+    }
+    reinterpret_cast<__nv_bfloat162*>(out + (long long)b * E + h * 64)[l] = __floats2bfloat162_rn(ox * inv, oy * inv);
+  }
 }
 
 // Copy the prefix K/V produced by the training-style prefill forward ([B*Lp, 3E] per layer) into
@@ -249,7 +269,8 @@ __global__ void __launch_bounds__(1024)
 sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ gen, int gen_ld,
                    int* __restrict__ j_ptr, int ban_specials, int V, int sent_len, float temperature,
                    int top_k, float top_p, float rep_penalty, unsigned long long seed,
-                   float* __restrict__ dbg_probs) {
+                   const unsigned long long* __restrict__ seed_dev, float* __restrict__ dbg_probs) {
+  if (seed_dev) seed = seed_dev[0];  // device-side seed: the launch stays CUDA-graph replayable
   extern __shared__ float s[];  // [V] working logits
   __shared__ ArgMax red[32];
   __shared__ float sv[MAX_SURV];
@@ -470,14 +491,14 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
     MMTG_TRY(decode_gemm(&a, stream));
   }
   const size_t layer_cache = (size_t)B * d.NH * Lmax * 64;
-  const int att_smem = 4 * Lmax * 4;
+  const int att_smem = (Lmax + 4 + 4 * 64) * 4;
   for (int l = 0; l < d.NL; ++l) {
     const mmtg_layer_offsets& lo = o.layer[l];
     MMTG_TRY(layernorm_fwd(w.h, P + lo.ln1_w, P + lo.ln1_b, w.x16, nullptr, nullptr, nullptr, B, E, eps, st));
     mmtg_gemm_args a = gemm(w.x16, E, W + lo.attn_w, 3 * E, true, 3 * E, E);
     a.out = w.qkv16; a.ldo = 3 * E; a.out_dtype = MMTG_BF16; a.bias = P + lo.attn_b;
     MMTG_TRY(decode_gemm(&a, stream));
-    decode_attn_kernel<<<cdiv(B * d.NH, 4), 128, att_smem, st>>>(
+    decode_attn_kernel<<<B * d.NH, 128, att_smem, st>>>(
         w.qkv16, w.kcache + l * layer_cache, w.vcache + l * layer_cache, w.keymask, j_ptr, w.att16, B, d.NH,
         d.P, Lmax);
     MMTG_LAUNCH_OK();
@@ -503,7 +524,8 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
 extern "C" int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_ld,
                                 int32_t* j_ptr, int32_t B, int32_t V, int32_t sent_len,
                                 float temperature, int32_t top_k, float top_p, float rep_penalty,
-                                uint64_t seed, int32_t ban_specials, float* dbg_probs, void* stream) {
+                                uint64_t seed, const uint64_t* seed_dev, int32_t ban_specials,
+                                float* dbg_probs, void* stream) {
   MMTG_CHECK_ARG(logits && gen && j_ptr && B > 0 && V > 102 && temperature > 0.f, "bad sampler args");
   MMTG_CHECK_ARG(top_k <= MAX_SURV, "top_k > %d not supported", MAX_SURV);
   static bool attr_set = false;
@@ -515,7 +537,8 @@ extern "C" int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, i
   MMTG_CHECK_ARG(smem <= 96 * 1024, "vocabulary too large for the sampler's shared-memory copy");
   cudaStream_t st = (cudaStream_t)stream;
   sample_rows_kernel<<<B, 1024, smem, st>>>(logits, ld, gen, gen_ld, j_ptr, ban_specials, V, sent_len, temperature,
-                                            top_k, top_p, rep_penalty, (unsigned long long)seed, dbg_probs);
+                                            top_k, top_p, rep_penalty, (unsigned long long)seed,
+                                            (const unsigned long long*)seed_dev, dbg_probs);
   MMTG_LAUNCH_OK();
   advance_kernel<<<1, 1, 0, st>>>(j_ptr);
   MMTG_LAUNCH_OK();

@@ -210,20 +210,35 @@ struct Gemm {
 };
 
 // wgrad: dW[rows, cols] += X^T Y with X [K, rows] and Y [K, cols] row-major activations.
-// Split-K picks enough work units to cover the machine (output tiles are few).
+// Output tiles are few (dW is at most 768 x 3072), so the reduction dimension (the tokens) is
+// split: pick the tile width and split count whose (tile pair x split) work units fill whole
+// waves of the 74 CTA-pair clusters, preferring fewer splits (fewer fp32 atomics) on ties.
 int wgrad(const bf16* X, long long ldx, const bf16* Y, long long ldy, float* dW, long long ldw,
           int rows, int cols, int K, cudaStream_t st) {
-  const int tiles = cdiv(rows, 128) * cdiv(cols, 128);
-  int split = 1;
-  if (tiles < num_sms()) {
-    split = cdiv(num_sms(), tiles);
-    const int max_split = (K + 511) / 512;  // keep >= 8 k-blocks per split
-    if (split > max_split) split = max_split;
-    if (split < 1) split = 1;
+  const int clusters = num_sms() / 2;
+  const int pairs = (cdiv(rows, 128) + 1) / 2;
+  const int nkb = cdiv(K, 64);
+  int best_bn = 128, best_split = 1;
+  double best_cost = 1e30;
+  for (int bn = 128; bn <= 256; bn += 128) {
+    if (bn == 256 && cols < 256) break;
+    const int units = pairs * cdiv(cols, bn);
+    const int max_split = nkb / 8 > 0 ? nkb / 8 : 1;  // keep >= 8 k-blocks per unit
+    for (int sp = 1; sp <= max_split && sp <= 16; ++sp) {
+      const int waves = cdiv(units * sp, clusters);
+      // time ~ waves x (k-blocks per unit x per-k-block cost(bn) + fixed tile cost)
+      const double kcost = bn == 256 ? 1.0 : 0.62;  // 128-wide tiles move more bytes per FLOP
+      const double cost = waves * (cdiv(nkb, sp) * kcost + 6.0) * (1.0 + 0.01 * sp);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_bn = bn;
+        best_split = sp;
+      }
+    }
   }
   Gemm g(X, ldx, true, Y, ldy, true, rows, cols, K);
-  g.out_f32(dW, ldw).accumulate(split);
-  g.a.block_n = 128;
+  g.out_f32(dW, ldw).accumulate(best_split);
+  g.a.block_n = best_bn;
   return g.run(st);
 }
 

@@ -46,7 +46,7 @@ def _filtered_distribution(logits2d, top_k, top_p, temperature=1.0, ban=True):
     dbg = torch.empty(Bn, 1024, 2, device=dev)
     _lib.check(_lib.lib().mmtg_sample_rows(C.c_void_p(z.data_ptr()), C.c_int64(z.stride(0)), C.c_void_p(gen.data_ptr()),
                                            4, C.c_void_p(j.data_ptr()), Bn, V, 1 << 20, C.c_float(temperature),
-                                           int(top_k), C.c_float(top_p), C.c_float(1.0), C.c_uint64(0), int(ban),
+                                           int(top_k), C.c_float(top_p), C.c_float(1.0), C.c_uint64(0), None, int(ban),
                                            C.c_void_p(dbg.data_ptr()), C.c_void_p(_lib.stream_ptr())),
                "mmtg_sample_rows")
     return dbg[..., 0], dbg[..., 1]
@@ -67,6 +67,24 @@ def returned_length(length, sent_len):
             continue
         i_last = i
     return i_last + 1
+
+
+class _DecodeSession:
+    """Per-(batch, length, sampling preset) decode state kept on the model: KV-cache workspace,
+    token / step-index / logits buffers and the captured CUDA graph of one decode step, so
+    repeated generation calls pay neither allocation nor capture."""
+
+    def __init__(self, model, d, length, Bn, dev, sampling):
+        lib = _lib.lib()
+        self.Lmax = d.P + length + 1
+        self.gen_ld = length + 1
+        self.dws = torch.empty(lib.mmtg_decode_workspace_bytes(C.byref(d), self.Lmax), dtype=torch.uint8, device=dev)
+        self.gen = torch.zeros(Bn, self.gen_ld, dtype=torch.int32, device=dev)
+        self.j = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seed = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_logits = torch.empty(Bn, d.V, device=dev)
+        self.graph = None
+        self.sampling = sampling
 
 
 @torch.no_grad()
@@ -101,25 +119,32 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
         model.train_flag = prev_flag
     step = logits0._mmtg_step
     d = step.dims
-    Lmax = d.P + length + 1
+    sampling = (float(temperature), int(top_k), float(top_p), float(repitition_penalty))
+    key = (Bn, length, str(dev), sampling, model._flat[0].data_ptr(), model._table(dev).data_ptr())
+    sessions = model.__dict__.setdefault("_decode_sessions", {})
+    ses = sessions.get(key)
+    if ses is None:
+        if len(sessions) > 4:
+            sessions.clear()
+        ses = sessions[key] = _DecodeSession(model, d, length, Bn, dev, sampling)
+    Lmax, gen_ld, dws, gen, j, step_logits = ses.Lmax, ses.gen_ld, ses.dws, ses.gen, ses.j, ses.step_logits
     st = C.c_void_p(_lib.stream_ptr())
-    nbytes = lib.mmtg_decode_workspace_bytes(C.byref(d), Lmax)
-    dws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     _lib.check(lib.mmtg_decode_load_prefix(C.byref(d), C.c_void_p(step.ws.data_ptr()), Lmax, C.c_void_p(dws.data_ptr()),
                                            C.c_void_p(step.mask.data_ptr()), st), "mmtg_decode_load_prefix")
-    gen_ld = length + 1
-    gen = torch.zeros(Bn, gen_ld, dtype=torch.int32, device=dev)
+    gen.zero_()
     gen[:, 0] = first[:, 0].to(torch.int32)
-    j = torch.zeros(1, dtype=torch.int32, device=dev)
-    step_logits = torch.empty(Bn, d.V, device=dev)
+    j.zero_()
+    ses.seed.fill_(int(seed))
     cm = model._c_model(d, dev)
+    ses.cm = cm  # keep the struct alive for captured launches
     kept = []
 
     def sample(ptr, ld):
         _lib.check(lib.mmtg_sample_rows(C.c_void_p(ptr), C.c_int64(ld), C.c_void_p(gen.data_ptr()), gen_ld,
                                         C.c_void_p(j.data_ptr()), Bn, d.V, sent_len, C.c_float(temperature),
                                         int(top_k), C.c_float(top_p), C.c_float(repitition_penalty),
-                                        C.c_uint64(seed), 1, None, C.c_void_p(_lib.stream_ptr())), "mmtg_sample_rows")
+                                        C.c_uint64(0), C.c_void_p(ses.seed.data_ptr()), 1, None,
+                                        C.c_void_p(_lib.stream_ptr())), "mmtg_sample_rows")
 
     def one_step():
         _lib.check(lib.mmtg_decode_step(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), C.c_void_p(gen.data_ptr()),
@@ -133,13 +158,11 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
         kept.append(logits0[:, -1, :].clone())
     sample(logits0.data_ptr() + 4 * (d.L - 1) * d.V, d.L * d.V)
     remaining = length - 1
-    eager = min(remaining, 2 if (use_cuda_graph and not return_step_logits) else remaining)
-    for _ in range(eager):
-        one_step()
-        if return_step_logits:
-            kept.append(step_logits.clone())
-    remaining -= eager
-    if remaining > 0:
+    graphed = use_cuda_graph and not return_step_logits
+    if graphed and ses.graph is None and remaining > 2:
+        for _ in range(2):  # eager warm-up (kernel attributes, descriptor cache), then capture
+            one_step()
+        remaining -= 2
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -147,8 +170,15 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
             with torch.cuda.graph(graph, stream=side):
                 one_step()
         torch.cuda.current_stream().wait_stream(side)
+        ses.graph = graph
+    if graphed and ses.graph is not None:
         for _ in range(remaining):
-            graph.replay()
+            ses.graph.replay()
+    else:
+        for _ in range(remaining):
+            one_step()
+            if return_step_logits:
+                kept.append(step_logits.clone())
     out = gen.cpu().numpy()
     n_ret = returned_length(length, sent_len)
     rows = [out[b, :n_ret].tolist() for b in range(Bn)]
