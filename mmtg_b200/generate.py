@@ -193,3 +193,22 @@ def sample_sequence(model, start_input, length, tokenizer=None, temperature=1.0,
     one = {k: np.asarray(v)[None] for k, v in start_input.items() if k != "rating"}
     return sample_sequence_batch(model, one, length, tokenizer, temperature, top_k, top_p, repitition_penalty,
                                  device, seed)[0]
+
+
+def postprocess_tokens(tokens):
+    """Detokenised generation -> lyric string (restates src/generate.py:222-236):
+    cut after the 10th [#EOS#] (if no [SEP] precedes the last [#EOS#]) or at the first [SEP],
+    drop [SEP] / [PAD] / [#START#], turn [#EOS#] into the Chinese comma and strip trailing commas.
+    `tokens`: list of token strings (tokenizer.convert_ids_to_tokens of sample_sequence's ids)."""
+    preds = list(tokens)
+    eos = [i for i, v in enumerate(preds) if v == "[#EOS#]"]
+    if len(eos) >= 10 and "[SEP]" not in preds[:eos[-1]]:
+        preds = preds[:eos[9] + 1] + ["[SEP]"]
+    elif "[SEP]" in preds:
+        preds = preds[:preds.index("[SEP]") + 1]
+    else:
+        preds = preds + ["[SEP]"]
+    text = "".join(preds).replace("[SEP]", "").replace("[PAD]", "").replace("[#START#]", "").replace("[#EOS#]", "，")
+    while text and text[-1] == "，":
+        text = text[:-1]
+    return text

@@ -480,10 +480,12 @@ class MMTG(nn.Module):
         return step.scalars[0], step.scalars[1], step.logits
 
     # ------------------------------------------------------------------------------------------
-    def fused_forward_loss(self, batch, stage, alpha=0.2):
+    def fused_forward_loss(self, batch, stage, alpha=0.2, grad_scale=1.0):
         """forward + MyLoss + the bf16 dlogits operand, WITHOUT torch.autograd: the same engine
         entry points `forward()` / `MyLoss` use, driven directly (restates src/train.py:188-192).
-        Returns (step, total, loss, kl); `backward_stages(step, ...)` completes the step."""
+        Returns (step, total, loss, kl); `backward_stages(step, ...)` completes the step.
+        `grad_scale` multiplies d(total) (ragged data-parallel batches: B_local / B_global with a
+        SUM all-reduce)."""
         prev = torch.is_grad_enabled()
         torch.set_grad_enabled(False)
         try:
@@ -508,9 +510,10 @@ class MMTG(nn.Module):
             self._unit = torch.ones(1, device=dev)
             self._alpha_buf = torch.zeros(1, device=dev)
             self._alpha_val = None
-        if self._alpha_val != alpha:
-            self._alpha_buf.fill_(alpha)
-            self._alpha_val = alpha
+        if self._alpha_val != (alpha, grad_scale):
+            self._unit.fill_(grad_scale)
+            self._alpha_buf.fill_(alpha * grad_scale)
+            self._alpha_val = (alpha, grad_scale)
         _lib.check(lib.mmtg_ce_bwd(vp(logits.data_ptr()), C.c_int64(d.V), vp(step.lse_ptr), None,
                                    vp(step.targets.data_ptr()), vp(coef.data_ptr()), vp(self._unit.data_ptr()),
                                    None, vp(step.dlogits_ptr), 1, C.c_int64(d.Vp), d.B, d.L, d.P, d.T, d.V, st),
@@ -528,11 +531,11 @@ class MMTG(nn.Module):
                                                   C.c_int64(step.ws.numel()), C.c_void_p(self._alpha_buf.data_ptr()),
                                                   s0, s1, C.c_void_p(_lib.stream_ptr())), "mmtg_train_backward")
 
-    def fused_train_step(self, batch, stage, alpha=0.2):
+    def fused_train_step(self, batch, stage, alpha=0.2, grad_scale=1.0):
         """fused_forward_loss + all backward stages (+ bucketed gradient all-reduce when
         `grad_sync` is set). No Python-side synchronisation and no autograd graph, so the call is
         CUDA-graph capturable (mmtg_b200.graph.GraphedTrainStep). Returns (total, loss, kl)."""
-        step, total, loss, kl = self.fused_forward_loss(batch, stage, alpha)
+        step, total, loss, kl = self.fused_forward_loss(batch, stage, alpha, grad_scale)
         _run_backward(step, self._alpha_buf)
         return total, loss, kl
 

@@ -5,7 +5,11 @@ stages (lm_head, block 11 .. block 0, embeddings/encoder); as soon as a stage ha
 gradients of one contiguous bucket of the flat gradient buffer (a GPT-2 block = 7.1 M params =
 28 MB fp32) that bucket is all-reduced (NCCL over NVLink/NVSwitch through torch.distributed) on a
 side stream while the next stage computes. There is no parameter broadcast and no logits gather.
-Equal per-rank batch sizes -> average; see DESIGN.md for the ragged (curriculum-filtered) case.
+Equal per-rank batch sizes -> average (default). Ragged per-rank batches (curriculum stages 1-2
+filter rows by rating, src/train.py:178-183): build `GradSync(average=False)` and scale each
+rank's loss gradient by `ragged_batch_scale(B_local)` = B_local / B_global
+(`MMTG.fused_train_step(..., grad_scale=...)`), so the SUM all-reduce reproduces the
+single-process gradient of the concatenated batch.
 """
 from __future__ import annotations
 
@@ -53,3 +57,12 @@ class GradSync:
     def finish(self, model):
         if self.world > 1 and self._cuda and model._flat[2].is_cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+
+def ragged_batch_scale(b_local: int, device=None, group=None) -> float:
+    """B_local / B_global for this step (one tiny integer all-reduce)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 1.0
+    t = torch.tensor([float(b_local)], device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(b_local) / float(t.item())

@@ -132,3 +132,24 @@ def test_fused_adamw_matches_hf_adamw_formula_on_paper():
         step = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
         p -= step * m / (v ** 0.5 + eps)
     assert abs(p - (0.5 - 3 * lr)) < 1e-5  # constant gradient -> |update| ~ lr per step
+
+
+def test_curriculum_filtering_matches_reference_rules():
+    from mmtg_b200.curriculum import filter_batch, stage_for_epoch, stage_row_indices
+    r = torch.tensor([3, 1, 5, 2, 4, 3, 5, 1])
+    assert stage_row_indices(r, 1).tolist() == [1, 7, 2, 6]        # r<2 first, then r>4
+    assert stage_row_indices(r, 2).tolist() == [1, 3, 7, 2, 4, 6]  # r<3 first, then r>3
+    assert stage_row_indices(r, 3).tolist() == list(range(8))
+    assert [stage_for_epoch(e, [1, 3]) for e in range(5)] == [1, 2, 2, 3, 3]  # train.sh: curriculums [1,3]
+    batch = {"rating": r, "targets": torch.arange(16).view(8, 2)}
+    out = filter_batch(batch, 1)
+    assert out["rating"].tolist() == [1, 1, 5, 5] and out["targets"][0].tolist() == [2, 3]
+    assert filter_batch({"rating": torch.tensor([3, 3])}, 2) is None
+
+
+def test_postprocess_tokens():
+    from mmtg_b200.generate import postprocess_tokens
+    sent = ["[#START#]", "a", "b", "[PAD]", "[#EOS#]"]
+    assert postprocess_tokens(sent * 10 + ["x", "y"]) == "，".join(["ab"] * 10)
+    assert postprocess_tokens(sent * 2 + ["[SEP]", "z"]) == "ab，ab"
+    assert postprocess_tokens(sent) == "ab"

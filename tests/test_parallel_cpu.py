@@ -44,6 +44,18 @@ def _worker(rank, world, port):
     assert torch.allclose(m._flat[2], torch.full_like(m._flat[2], expect))
     assert (touched == 1).all(), "every element must be reduced exactly once"
     assert sync.bytes_reduced == m._flat[2].numel() * 4
+    # ragged batches: SUM all-reduce of gradients pre-scaled by B_local / B_global
+    from mmtg_b200.parallel import ragged_batch_scale
+    b_local = 3 + 2 * rank  # 3 and 5 rows
+    scale = ragged_batch_scale(b_local)
+    assert abs(scale - b_local / 8.0) < 1e-9
+    m2 = _FakeModel(nl=2, per_layer=10, tail=7, rank=rank)
+    m2._flat[2].fill_(scale * (rank + 1))  # per-rank mean gradient (rank + 1), pre-scaled
+    s2 = GradSync(average=False)
+    for s in range(m2.nl + 2):
+        s2.after_stage(m2, s, m2.nl + 2)
+    want = (3 * 1 + 5 * 2) / 8.0  # gradient of the mean over the 8 concatenated rows
+    assert torch.allclose(m2._flat[2], torch.full_like(m2._flat[2], want))
     dist.destroy_process_group()
 
 
