@@ -335,8 +335,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint64_t* bar_sdp = bar_load + 1;   // S and dP of the current pair are in TMEM
   uint64_t* bar_pds = bar_load + 2;   // P and dS of the current pair are in shared memory (128 arrivals)
   uint64_t* bar_mma2 = bar_load + 3;  // dV/dK/dQ MMAs of the current pair have retired
-  uint64_t* bar_epi = bar_load + 4;   // dK_j/dV_j drained from TMEM (128 arrivals)
-  uint32_t* tmem_slot = (uint32_t*)(bar_load + 5);
+  uint64_t* bar_epi = bar_load + 4;   // dK_j/dV_j drained from TMEM (256 arrivals)
+  uint64_t* bar_load1 = bar_load + 5; // operand tiles of sequence block 1 (bar_load: block 0)
+  uint32_t* tmem_slot = (uint32_t*)(bar_load + 6);
   float* s_mask = (float*)(smem + BW_BAR + 64);  // [256] additive key mask
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,6 +348,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (threadIdx.x == 0) {
     mbar_init(bar_load, 1);
+    mbar_init(bar_load1, 1);
     mbar_init(bar_sdp, 1);
     mbar_init(bar_pds, 256);
     mbar_init(bar_mma2, 1);
@@ -372,23 +374,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     if (lane == 0) {
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_do);
-      mbar_arrive_expect_tx(bar_load, (uint32_t)(nb * 4 * 16384));
-      for (int i = 0; i < nb; ++i) {
-        tma_load_2d(smem + BW_Q + i * 16384, &tm_qkv, bar_load, h * 64, row0 + i * 128);
-        tma_load_2d(smem + BW_K + i * 16384, &tm_qkv, bar_load, p.E + h * 64, row0 + i * 128);
-        tma_load_2d(smem + BW_V + i * 16384, &tm_qkv, bar_load, 2 * p.E + h * 64, row0 + i * 128);
-        tma_load_2d(smem + BW_DO + i * 16384, &tm_do, bar_load, h * 64, row0 + i * 128);
+      for (int i = 0; i < nb; ++i) {  // block 0 first: its pair can start while block 1 streams in
+        uint64_t* bl = i == 0 ? bar_load : bar_load1;
+        mbar_arrive_expect_tx(bl, (uint32_t)(4 * 16384));
+        tma_load_2d(smem + BW_Q + i * 16384, &tm_qkv, bl, h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_K + i * 16384, &tm_qkv, bl, p.E + h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_V + i * 16384, &tm_qkv, bl, 2 * p.E + h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_DO + i * 16384, &tm_do, bl, h * 64, row0 + i * 128);
       }
       const uint32_t idesc_sp = umma_idesc_bf16(128, 128, 0, 0);  // S, dP: A K-major, B K-major
       const uint32_t idesc_kv = umma_idesc_bf16(128, 64, 1, 1);   // dV, dK: A (P/dS) MN-major, B MN-major
       const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ: A (dS) K-major, B (K) MN-major
       const uint32_t aP = smem_u32(smem + BW_P), aDS = smem_u32(smem + BW_DS);
       mbar_wait<21>(bar_load, 0);
+      bool have1 = false;
       int pair = 0;
       for (int j = 0; j < nb; ++j) {
         const uint32_t aK = smem_u32(smem + BW_K + j * 16384), aV = smem_u32(smem + BW_V + j * 16384);
         for (int i = j; i < nb; ++i, ++pair) {
           const uint32_t aQ = smem_u32(smem + BW_Q + i * 16384), aDO = smem_u32(smem + BW_DO + i * 16384);
+          if (i == 1 && !have1) {
+            mbar_wait<24>(bar_load1, 0);
+            have1 = true;
+          }
           // S/dP TMEM is free once the softmax threads have consumed the previous pair (bar_pds
           // of pair-1, waited below before the second-stage MMAs of that pair were issued).
           tc_fence_after();
@@ -429,17 +437,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const float sl2 = p.scale * LOG2E;
     uint8_t* prow = smem + BW_P + r * 128;
     uint8_t* dsrow = smem + BW_DS + r * 128;
+    // row statistics of both query blocks, fetched once while the operand tiles are in flight
+    float lse2_blk[2] = {INFINITY, INFINITY}, dl_blk[2] = {0.f, 0.f};  // +inf -> P = 0 beyond the sequence
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = i * 128 + r;
+      if (i < nb && q < p.L) {
+        const long long so = ((long long)b * p.NH + h) * p.L + q;
+        const float lv = __ldg(p.lse + so);
+        lse2_blk[i] = lv == -INFINITY ? INFINITY : lv * LOG2E;
+        dl_blk[i] = __ldg(p.delta + so);
+      }
+    }
     int pair = 0;
     for (int j = 0; j < nb; ++j) {
       for (int i = j; i < nb; ++i, ++pair) {
         const int q = i * 128 + r;
-        const long long so = ((long long)b * p.NH + h) * p.L + q;
-        float lse2 = INFINITY, dl = 0.f;  // +inf -> P = 0 for rows beyond the sequence
-        if (q < p.L) {
-          const float lv = p.lse[so];
-          lse2 = lv == -INFINITY ? INFINITY : lv * LOG2E;
-          dl = p.delta[so];
-        }
+        const float lse2 = i == 0 ? lse2_blk[0] : lse2_blk[1];
+        const float dl = i == 0 ? dl_blk[0] : dl_blk[1];
         mbar_wait<25>(bar_sdp, (uint32_t)(pair & 1));
         if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
         tc_fence_after();

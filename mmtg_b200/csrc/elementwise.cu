@@ -90,13 +90,14 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
   const int c = threadIdx.x * 2;
   const float2 gam2 = *reinterpret_cast<const float2*>(gamma + c);
   float2 adg = make_float2(0.f, 0.f), adb = adg, acs = adg;
-  const int ntiles = cdiv(M, TR);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r0 = tile * TR;
+  // each block owns ONE contiguous row range (balanced single wave), walked in tiles of TR rows
+  const int rows_per_block = cdiv(M, (int)gridDim.x);
+  const int r_begin = blockIdx.x * rows_per_block, r_end = min(M, r_begin + rows_per_block);
+  for (int r0 = r_begin; r0 < r_end; r0 += TR) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int rl = warp * 2 + k, row = r0 + rl;
-      if (row < M) {
+      if (row < r_end) {
         const float mu = mean[row], rs = rstd[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -128,7 +129,7 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
       }
     }
     __syncthreads();
-    const int nr = min(TR, M - r0);
+    const int nr = min(TR, r_end - r0);
 #pragma unroll 4
     for (int rl = 0; rl < nr; ++rl) {
       const long long off = (long long)(r0 + rl) * E + c;
@@ -350,8 +351,8 @@ int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean
                   const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
                   bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st) {
   MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
-  const int tile_rows = 2 * (E / 64);
-  const int blocks = min(cdiv(M, tile_rows), num_sms() * 4);
+  // 3 blocks of E/2 threads are resident per SM (56 registers): one balanced wave
+  const int blocks = max(1, min(M, num_sms() * 3));
   ProfScope prof(2, 0, (double)M * E * (4 + (dy_bf16 ? 2 : 4) + 4 + (accumulate_dx ? 4 : 0) + (dx16 ? 2 : 0)), st);
 #define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, EE / 2, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, dx16, dx_colsum, M)
   if (E == 768) { if (dy_bf16) LNB(768, true); else LNB(768, false); }

@@ -104,6 +104,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // let the next PDL-launched kernel of the stream be scheduled as soon as SMs free up (it
+  // blocks in its own griddepcontrol.wait until this grid has fully completed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -135,6 +139,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   cluster_sync_all();  // peer barriers must be initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel
+  // of the stream was still draining (its prologue above overlapped that tail); nothing below
+  // may touch global memory before the previous grid has completed and flushed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const uint32_t crank = cluster_ctarank();       // 0 / 1 within the pair
   const int cluster_id = blockIdx.x >> 1;
@@ -692,13 +700,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  static const bool use_pdl = []() {  // MMTG_GEMM_PDL=0 disables programmatic dependent launch
+    const char* e = getenv("MMTG_GEMM_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl ? 2 : 1;
   MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, TWO>, tmA, tmB, p));
   MMTG_LAUNCH_OK();
   count_launch();
