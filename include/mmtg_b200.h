@@ -242,6 +242,18 @@ int mmtg_decode_load_prefix(const mmtg_dims* dims_prefix, void* train_workspace,
 int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_workspace, const int32_t* gen,
                      int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
                      float* logits, void* stream);
+/* Fused form of mmtg_decode_step for B <= 64, E = 768: ONE persistent kernel runs every decoder
+ * block + ln_f + lm_head of the position (grid-wide barriers between phases, weights and cached
+ * K/V prefetched one phase ahead, LayerNorm folded into the following linear layer). Same
+ * arguments and results as mmtg_decode_step up to fp32 summation order (split-K partials are
+ * combined with atomic adds). Requires mmtg_decode_fold_weights on this workspace after every
+ * change of the weights. */
+int mmtg_decode_fold_weights(const mmtg_model* m, int32_t Lmax, void* decode_workspace, void* stream);
+int mmtg_decode_step_fused(const mmtg_model* m, int32_t Lmax, void* decode_workspace, const int32_t* gen,
+                           int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
+                           float* logits, void* stream);
+/* Debug: per-phase globaltimer stamps of the fused step (CTA 0) into dev_buf (>= 80 x u64). */
+int mmtg_decode_set_trace(uint64_t* dev_buf);
 /* ban_specials: set ids 1, 2, 100, 102 to -inf (src/generate.py:133-136).
  * seed_dev (optional, device): overrides `seed`, so a captured launch can be re-seeded.
  * dbg_probs (optional): [B, 1024, 2] (kept token id, probability) of the filtered distribution */

@@ -39,6 +39,7 @@ struct DWs {
   int* posidx;            // [B]
   bf16 *emb16, *p1, *x16, *qkv16, *att16, *a16;
   float *h, *h2;
+  MegaBufs mega;  // fused step: accumulators, folded weights, grid barrier
   size_t bytes;
 };
 
@@ -65,6 +66,17 @@ void carve_decode(const mmtg_dims& d, int Lmax, uint8_t* base, DWs* w) {
   w->a16 = (bf16*)take(B * 4 * E * 2);
   w->h = (float*)take(B * E * 4);
   w->h2 = (float*)take(B * E * 4);
+  MegaBufs& g = w->mega;
+  g.h = w->h; g.h2 = w->h2; g.att16 = w->att16; g.kcache = w->kcache; g.vcache = w->vcache; g.keymask = w->keymask;
+  g.h_alt = (float*)take(B * E * 4);
+  g.qkv_acc = (float*)take(B * 3 * E * 4);
+  g.u_acc = (float*)take(B * 4 * E * 4);
+  g.row_stats = (float*)take(2 * 64 * 2 * 4);
+  g.barrier = (unsigned int*)take(256);
+  g.f_attn = (bf16*)take((size_t)d.NL * E * 3 * E * 2);
+  g.f_fc = (bf16*)take((size_t)d.NL * E * 4 * E * 2);
+  g.f_wte = (bf16*)take((size_t)d.V * E * 2);
+  g.f_vec = (float*)take(((size_t)d.NL * 14 * E + 2 * (size_t)d.V) * 4);
   w->bytes = off;
 }
 
@@ -75,8 +87,9 @@ decode_prep_kernel(const int* __restrict__ gen, int gen_ld, const int* __restric
                    const float* __restrict__ table, const float* __restrict__ ctx,
                    bf16* __restrict__ emb16, int* __restrict__ types, int* __restrict__ posidx,
                    int* __restrict__ keymask, int B, int P, int S, int sent_len, int n_sent, int D,
-                   int Lmax) {
+                   int Lmax, unsigned int* __restrict__ barrier) {
   const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0) *barrier = 0u;  // the megakernel's grid barrier starts from zero
   const int j = *j_ptr;
   const int tok = gen[b * gen_ld + j];
   if (threadIdx.x == 0) {
@@ -442,6 +455,11 @@ int decode_load_prefix(const mmtg_dims& d, const bf16* const* qkv_layers, const 
   DWs w;
   carve_decode(d, Lmax, (uint8_t*)decode_ws, &w);
   const size_t layer_cache = (size_t)d.B * d.NH * Lmax * 64;
+  // fused step: the qkv accumulator starts from zero (each position leaves it zeroed again); cache
+  // rows past the current position are read as whole 64-key boxes and must hold finite values
+  MMTG_CUDA_OK(cudaMemsetAsync(w.mega.qkv_acc, 0, (size_t)d.B * 3 * d.E * 4, st));
+  MMTG_CUDA_OK(cudaMemsetAsync(w.kcache, 0, (size_t)d.NL * layer_cache * 2, st));
+  MMTG_CUDA_OK(cudaMemsetAsync(w.vcache, 0, (size_t)d.NL * layer_cache * 2, st));
   for (int l = 0; l < d.NL; ++l) {
     dim3 grid(d.B * d.L, d.NH);
     kv_scatter_kernel<<<grid, 32, 0, st>>>(qkv_layers[l], w.kcache + l * layer_cache,
@@ -456,9 +474,11 @@ int decode_load_prefix(const mmtg_dims& d, const bf16* const* qkv_layers, const 
 }
 }  // namespace mmtg
 
-extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_ws, const int32_t* gen,
-                                int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
-                                float* logits, void* stream) {
+namespace mmtg {
+namespace {
+int decode_step_impl(const mmtg_model* m, int32_t Lmax, void* decode_ws, const int32_t* gen, int32_t gen_ld,
+                     const int32_t* j_ptr, int32_t sent_len, int32_t n_sent, float* logits, void* stream,
+                     bool fused) {
   MMTG_CHECK_ARG(m && decode_ws && gen && j_ptr && logits, "null argument");
   const mmtg_dims& d = m->dims;
   DWs w;
@@ -470,7 +490,7 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
   const int B = d.B, E = d.E, He = d.He, Dw = d.Dw;
   const float eps = 1e-5f;
   decode_prep_kernel<<<B, 256, 0, st>>>(gen, gen_ld, j_ptr, m->token_table, w.ctx, w.emb16, w.types,
-                                        w.posidx, w.keymask, B, d.P, d.S, sent_len, n_sent, Dw, Lmax);
+                                        w.posidx, w.keymask, B, d.P, d.S, sent_len, n_sent, Dw, Lmax, w.mega.barrier);
   MMTG_LAUNCH_OK();
   count_launch();
   auto gemm = [&](const bf16* A, long long lda, const bf16* Bm, long long ldb, bool b_mn, int N, int K) {
@@ -490,6 +510,7 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
     a.rowtab1 = P + o.wte; a.ldt1 = E; a.rowidx1 = w.types;
     MMTG_TRY(decode_gemm(&a, stream));
   }
+  if (fused) return decode_mega_launch(m, Lmax, w.mega, j_ptr, logits, st);
   const size_t layer_cache = (size_t)B * d.NH * Lmax * 64;
   const int att_smem = (Lmax + 4 + 4 * 64) * 4;
   for (int l = 0; l < d.NL; ++l) {
@@ -519,6 +540,29 @@ extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_
   a.out = logits; a.ldo = d.V; a.out_dtype = MMTG_F32;
   MMTG_TRY(decode_gemm(&a, stream));
   return 0;
+}
+}  // namespace
+}  // namespace mmtg
+
+extern "C" int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_ws, const int32_t* gen,
+                                int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
+                                float* logits, void* stream) {
+  return decode_step_impl(m, Lmax, decode_ws, gen, gen_ld, j_ptr, sent_len, n_sent, logits, stream, false);
+}
+
+extern "C" int mmtg_decode_step_fused(const mmtg_model* m, int32_t Lmax, void* decode_ws, const int32_t* gen,
+                                      int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
+                                      float* logits, void* stream) {
+  MMTG_CHECK_ARG(m && m->dims.B <= 64 && m->dims.E == 768 && m->dims.NH * 64 == m->dims.E && Lmax <= 1024,
+                 "fused decode step supports B <= 64, E = 768, head dim 64, Lmax <= 1024");
+  return decode_step_impl(m, Lmax, decode_ws, gen, gen_ld, j_ptr, sent_len, n_sent, logits, stream, true);
+}
+
+extern "C" int mmtg_decode_fold_weights(const mmtg_model* m, int32_t Lmax, void* decode_ws, void* stream) {
+  MMTG_CHECK_ARG(m && decode_ws && m->params, "null argument");
+  DWs w;
+  carve_decode(m->dims, Lmax, (uint8_t*)decode_ws, &w);
+  return decode_fold_weights(m, w.mega, (cudaStream_t)stream);
 }
 
 extern "C" int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_ld,

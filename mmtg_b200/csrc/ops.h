@@ -51,4 +51,20 @@ int beta_bwd(const float* topic, const float* img, const float* txt, const float
              const float* att, const bf16* do16, float* dtopic, float* dimg, float* dtxt,
              float* datt_w, float* datt_b, int B, int S, int H, cudaStream_t st);
 
+// decode_mega.cu: buffers of the fused decode step (carved from the decode workspace)
+struct MegaBufs {
+  float *h, *h_alt, *h2, *qkv_acc, *u_acc;
+  float* row_stats;  // [2][64][2]: (mean, rstd) of h rows, then of h2 rows
+  bf16* att16;
+  bf16 *kcache, *vcache;
+  const int* keymask;
+  unsigned int* barrier;
+  // LayerNorm-folded weights (mmtg_decode_fold_weights)
+  bf16 *f_attn, *f_fc, *f_wte;  // [NL][E][3E], [NL][E][4E], [V][E]
+  float* f_vec;                 // per layer: cs_attn[3E] b_attn[3E] cs_fc[4E] b_fc[4E]; then cs_head[V] b_head[V]
+};
+int decode_mega_launch(const mmtg_model* m, int Lmax, const MegaBufs& bufs, const int* j_ptr, float* logits,
+                       cudaStream_t st);
+int decode_fold_weights(const mmtg_model* m, const MegaBufs& bufs, cudaStream_t st);
+
 }  // namespace mmtg

@@ -12,6 +12,8 @@ batch-1 reference runs at once (BASELINE.json configs[3]: batch 64).
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -87,6 +89,26 @@ class _DecodeSession:
         self.sampling = sampling
 
 
+class _SectionTimer:
+    """MMTG_GEN_TIMING=1: print synchronized wall time of each section of a generation call."""
+
+    def __init__(self):
+        self.on = os.environ.get("MMTG_GEN_TIMING") == "1"
+        self.t = time.perf_counter()
+        self.rows = []
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.rows.append(f"{name} {1e3 * (now - self.t):.2f} ms")
+            self.t = now
+
+    def done(self):
+        if self.on:
+            print("[mmtg generate] " + " | ".join(self.rows), flush=True)
+
+
 @torch.no_grad()
 def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperature=1.0, top_k=30, top_p=0.0,
                           repitition_penalty=1.0, device="cuda", seed=0, use_cuda_graph=True,
@@ -98,6 +120,7 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
     if dev.type != "cuda":
         raise _lib.MMTGError("mmtg_b200 generation runs on CUDA only (no CPU fallback)")
     lib = _lib.lib()
+    tm = _SectionTimer()
     host = _collate(start_inputs)
     Bn = host["topic_ids"].shape[0]
     batch = {k: torch.as_tensor(host[k], dtype=torch.float32).to(dev) for k in _FLOAT_KEYS}
@@ -110,6 +133,7 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
     dc = model.data_config
     sent_len = dc["max_sent_length"] + 2
     n_sent = dc["max_seq_length"] // sent_len
+    tm.mark("collate+h2d")
     # ---- prefill: [prompt | first token] through the training-style engine (inference branch) ----
     prev_flag = model.train_flag
     model.train_flag = False
@@ -117,10 +141,13 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
         _, _, logits0 = model(batch)
     finally:
         model.train_flag = prev_flag
+    tm.mark("prefill")
     step = logits0._mmtg_step
     d = step.dims
     sampling = (float(temperature), int(top_k), float(top_p), float(repitition_penalty))
-    key = (Bn, length, str(dev), sampling, model._flat[0].data_ptr(), model._table(dev).data_ptr())
+    # fused persistent-kernel step for B <= 64 (MMTG_DECODE_MEGA=0 selects the per-op launches)
+    fused = Bn <= 64 and d.E == 768 and d.P + length + 1 <= 1024 and os.environ.get("MMTG_DECODE_MEGA", "1") != "0"
+    key = (Bn, length, str(dev), sampling, model._flat[0].data_ptr(), model._table(dev).data_ptr(), fused)
     sessions = model.__dict__.setdefault("_decode_sessions", {})
     ses = sessions.get(key)
     if ses is None:
@@ -131,6 +158,7 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
     st = C.c_void_p(_lib.stream_ptr())
     _lib.check(lib.mmtg_decode_load_prefix(C.byref(d), C.c_void_p(step.ws.data_ptr()), Lmax, C.c_void_p(dws.data_ptr()),
                                            C.c_void_p(step.mask.data_ptr()), st), "mmtg_decode_load_prefix")
+    tm.mark("session+load_prefix")
     gen.zero_()
     gen[:, 0] = first[:, 0].to(torch.int32)
     j.zero_()
@@ -146,13 +174,19 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
                                         C.c_uint64(0), C.c_void_p(ses.seed.data_ptr()), 1, None,
                                         C.c_void_p(_lib.stream_ptr())), "mmtg_sample_rows")
 
+    step_fn = lib.mmtg_decode_step_fused if fused else lib.mmtg_decode_step
+    if fused:  # LayerNorm-folded weight copies follow the current parameters
+        _lib.check(lib.mmtg_decode_fold_weights(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), st),
+                   "mmtg_decode_fold_weights")
+
     def one_step():
-        _lib.check(lib.mmtg_decode_step(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), C.c_void_p(gen.data_ptr()),
-                                        gen_ld, C.c_void_p(j.data_ptr()), sent_len, n_sent,
-                                        C.c_void_p(step_logits.data_ptr()), C.c_void_p(_lib.stream_ptr())),
+        _lib.check(step_fn(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), C.c_void_p(gen.data_ptr()),
+                           gen_ld, C.c_void_p(j.data_ptr()), sent_len, n_sent,
+                           C.c_void_p(step_logits.data_ptr()), C.c_void_p(_lib.stream_ptr())),
                    "mmtg_decode_step")
         sample(step_logits.data_ptr(), d.V)
 
+    tm.mark("fold")
     # reference iteration i = 0: logits of the last prefix row decide targets[1]
     if return_step_logits:
         kept.append(logits0[:, -1, :].clone())
@@ -179,7 +213,10 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
             one_step()
             if return_step_logits:
                 kept.append(step_logits.clone())
+    tm.mark("steps")
     out = gen.cpu().numpy()
+    tm.mark("d2h")
+    tm.done()
     n_ret = returned_length(length, sent_len)
     rows = [out[b, :n_ret].tolist() for b in range(Bn)]
     if return_step_logits:

@@ -401,6 +401,9 @@ class MMTG(nn.Module):
         if d._table_host is None:
             raise _lib.MMTGError("token table missing: pass token_table=... or call "
                                  "model.decoder.set_token_table(...) / load_token_id2emb(path)")
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:  # "cuda" and "cuda:<current>" are one device
+            device = torch.device("cuda", torch.cuda.current_device())
         if getattr(d, "_table_dev", None) is None or d._table_dev.device != device:
             d._table_dev = d._table_host.to(device)
         return d._table_dev

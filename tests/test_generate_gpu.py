@@ -63,17 +63,64 @@ def test_greedy_matches_reference_golden(world, cuda):
         assert rows[0] == ref_ids
 
 
-def test_graph_replay_equals_eager_and_batch_rows_independent(world, cuda):
+def _first_near_tie(step_logits, row, eps):
+    """Index of the first generated position whose top-1/top-2 logit margin is <= eps."""
+    for i, lg in enumerate(step_logits):
+        top = torch.topk(lg[row].float(), 2).values
+        if (top[0] - top[1]).item() <= eps:
+            return i
+    return len(step_logits)
+
+
+@pytest.mark.parametrize("path", ["per_op", "fused"])
+def test_graph_replay_equals_eager_and_batch_rows_independent(world, cuda, monkeypatch, path):
+    """Per-op launches are deterministic: graph replay, eager and batch-1 runs give identical ids.
+    The fused persistent kernel combines split-K partials with atomic adds, so its logits move
+    in the last bits between runs: ids must agree up to the first top-2 near-tie."""
     from mmtg_b200.generate import sample_sequence_batch
     model, sd, table = world
+    monkeypatch.setenv("MMTG_DECODE_MEGA", "0" if path == "per_op" else "1")
     starts = [_start(s) for s in (99, 7, 21)]
     kw = dict(temperature=1.0, top_k=1, top_p=0.0, repitition_penalty=1.0, device="cuda")
     a = sample_sequence_batch(model, starts, 60, use_cuda_graph=True, **kw)
-    b = sample_sequence_batch(model, starts, 60, use_cuda_graph=False, **kw)
-    assert a == b
-    for i, s in enumerate(starts):
-        assert sample_sequence_batch(model, [s], 60, use_cuda_graph=True, **kw)[0] == a[i]
+    b, blog = sample_sequence_batch(model, starts, 60, use_cuda_graph=False, return_step_logits=True, **kw)
     assert len(a[0]) == 60  # targets[:i_last + 1] with i_last = 59 (not a forced slot)
+    singles = [sample_sequence_batch(model, [s], 60, use_cuda_graph=True, **kw)[0] for s in starts]
+    if path == "per_op":
+        assert a == b
+        assert singles == a
+        return
+    for i in range(len(starts)):
+        # generated position k+1 is decided by step logits k; forced slots are equal by construction
+        safe = _first_near_tie(blog, i, 2e-3) + 1
+        assert safe >= 8, f"row {i}: near-tie already at step {safe - 1}"
+        assert a[i][:safe] == b[i][:safe], (i, safe)
+        assert singles[i][:safe] == b[i][:safe], (i, safe)
+
+
+def test_fused_step_matches_per_op_step(world, cuda, monkeypatch):
+    """The persistent-kernel step (LayerNorm folded into the weights, atomics) and the per-op
+    step give the same logits for the same history."""
+    from mmtg_b200.generate import sample_sequence_batch
+    model, sd, table = world
+    starts = [_start(s) for s in (3, 14)]
+    kw = dict(temperature=1.0, top_k=1, top_p=0.0, repitition_penalty=1.0, device="cuda", return_step_logits=True)
+    monkeypatch.setenv("MMTG_DECODE_MEGA", "0")
+    ra, la = sample_sequence_batch(model, starts, 120, **kw)
+    monkeypatch.setenv("MMTG_DECODE_MEGA", "1")
+    rb, lb = sample_sequence_batch(model, starts, 120, **kw)
+    compared = 0
+    for i in range(len(starts)):
+        same = 0
+        while same < len(ra[i]) and ra[i][same] == rb[i][same]:
+            same += 1
+        # step logits k depend on tokens 0..k only
+        n = min(same, len(la), len(lb))
+        for k in range(1, n):
+            d = (la[k][i] - lb[k][i]).abs()
+            assert d.max().item() <= 0.03 and d.mean().item() <= 0.005, (i, k, d.max().item())
+        compared += n
+    assert compared >= 60, compared
 
 
 def test_kv_cache_equals_full_recompute(world, cuda):
