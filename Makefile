@@ -8,7 +8,7 @@ LIB := mmtg_b200/lib/libmmtg_b200.so
 
 all: $(LIB)
 
-build/%.o: mmtg_b200/csrc/%.cu mmtg_b200/csrc/common.cuh include/mmtg_b200.h
+build/%.o: mmtg_b200/csrc/%.cu $(wildcard mmtg_b200/csrc/*.cuh) $(wildcard mmtg_b200/csrc/*.h) include/mmtg_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 

@@ -132,6 +132,8 @@ def main():
     ap.add_argument("--impl", default="mmtg_b200")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="GPT-2 embd/resid/attn dropout of the training forward (reference default 0.1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,6 +163,8 @@ def main():
     table = synth.make_token_table()
     model = MMTG(model_cfgs, data_config(), 13317, train_flag=True, token_table=table)
     model.load_state_dict(synth.make_state_dict(0))  # identical replicas on every rank
+    model.set_dropout(args.dropout, args.dropout, args.dropout)
+    model.set_dropout_seed(0x5EED + 7919 * rank)  # independent masks per data-parallel rank
     model.to(dev)
     if world > 1:
         model.grad_sync = GradSync()
@@ -292,7 +296,7 @@ def main():
             "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "MMTG train step (fwd + MyLoss stage 3 + 0.2*KL, bwd, clip 1.0, AdamW) bf16 GEMMs / fp32 master+residual, batch 32 per GPU, L=236, V=13317 (BASELINE.json configs[1]); dropout p=0",
+            "config": {"workload": "MMTG train step (fwd + MyLoss stage 3 + 0.2*KL, bwd, clip 1.0, AdamW) bf16 GEMMs / fp32 master+residual, batch 32 per GPU, L=236, V=13317 (BASELINE.json configs[1]); GPT-2 embd/resid/attn dropout p=%g (fused counter-based masks)" % args.dropout,
                        "global_batch": global_batch, "seq_len": 236,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "launch": "cuda_graph" if use_graph else "eager",

@@ -96,6 +96,13 @@ typedef struct mmtg_gemm_args {
   /* 0: out2 receives the pre-activation value; 1 (with MMTG_ACT_GELU_NEW): out2 receives
    * gelu_new'(pre-activation), so the backward epilogue is a single multiply */
   int32_t out2_mode;
+  /* inverted dropout of the value (after bias / activation / row-table adds, BEFORE the residual
+   * add): element (row, col) is kept iff the counter-based mask of (*drop_seed, drop_site,
+   * row * N + col) says so (mmtg_dropout_mask gives the same mask). drop_p = 0 or NULL seed: off.
+   * Needs N % 4 == 0 and 16-byte aligned operands. */
+  const uint64_t* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
 } mmtg_gemm_args;
 
 int mmtg_gemm_bf16(const mmtg_gemm_args* args, void* stream);
@@ -198,6 +205,13 @@ typedef struct mmtg_model {
   const void* params_bf16;  /* flat bf16 shadow (same offsets) */
   float* grads;             /* flat fp32 gradients (same offsets), accumulated into */
   const float* token_table; /* [V, Dw] fp32, frozen (vocab/token_id2emb_dict.pkl) */
+  /* GPT-2 dropout of the training forward (HF configuration_gpt2.py embd_pdrop / resid_pdrop /
+   * attn_pdrop, live in train mode: SURVEY §5). Masks are counter-based functions of
+   * (*drop_seed, site, element index): backward regenerates them, nothing is stored. The caller
+   * changes *drop_seed between steps (mmtg_dropout_next_seed). All p = 0 or NULL seed: off. */
+  const uint64_t* drop_seed;
+  float p_embd, p_resid, p_attn;
+  int32_t _pad_drop;
 } mmtg_model;
 
 typedef struct mmtg_batch {
@@ -226,6 +240,19 @@ int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, void* workspac
                         int64_t workspace_bytes, const float* g_kl, int32_t stage_begin,
                         int32_t stage_end, void* stream);
 int mmtg_dlogits_from_f32(const mmtg_dims* dims, void* workspace, const float* dlogits_f32, void* stream);
+
+/* Dropout sites: block l uses 4*l + {0: attention probabilities [B,NH,L,L'] with L' = L rounded
+ * up to even, 1: attention c_proj output [B*L,E], 2: mlp c_proj output}; MMTG_DROP_SITE_EMBD is
+ * the embedding sum [B*L,E]. mmtg_dropout_mask materialises keep flags (1 = kept) of elements
+ * [0, n) of a site for tests; mmtg_dropout_next_seed advances the device-side seed (capturable). */
+int mmtg_attn_fwd_drop(const void* qkv, const int32_t* key_mask, void* out, float* lse, int32_t B, int32_t L,
+                       int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p, void* stream);
+int mmtg_attn_bwd_drop(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,
+                       const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L, int32_t n_head,
+                       const uint64_t* seed_dev, uint32_t site, float p, void* stream);
+#define MMTG_DROP_SITE_EMBD 0xFFFFu
+int mmtg_dropout_mask(const uint64_t* seed_dev, uint32_t site, float p, int64_t n, uint8_t* keep_out, void* stream);
+int mmtg_dropout_next_seed(uint64_t* seed_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * KV-cached generation: the per-token body of sample_sequence (src/generate.py:117-142) and the

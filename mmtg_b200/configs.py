@@ -39,6 +39,11 @@ GPT2_CONFIG = {
     "n_layer": 12,
     "n_positions": 1024,
     "vocab_size": 13317,
+    # HF GPT2Config defaults (configuration_gpt2.py); config/model_config.json does not override
+    # them, so they are live in the reference's training forward
+    "embd_pdrop": 0.1,
+    "resid_pdrop": 0.1,
+    "attn_pdrop": 0.1,
 }
 
 

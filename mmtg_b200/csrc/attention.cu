@@ -11,7 +11,7 @@
 #include <stdlib.h>
 
 #include "../../include/mmtg_b200.h"
-#include "common.cuh"
+#include "ops.h"
 #include "mma_tiles.cuh"
 
 namespace mmtg {
@@ -415,17 +415,19 @@ attn_bwd_dq_kernel(const AttnParams p) {
 void count_launch(int n = 1);
 
 int attn_fwd_tc(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
-                cudaStream_t st);
+                cudaStream_t st, const DropSpec* drop);
+static inline bool drop_on(const DropSpec* d) { return d && d->seed && d->p > 0.f; }
 
 // impl: 0 = default (tcgen05 unless MMTG_ATTN_TC=0), 1 = mma.sync kernels, 2 = tcgen05 kernels
 int attn_fwd_impl(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
-                  int impl, cudaStream_t st) {
+                  int impl, cudaStream_t st, const DropSpec* drop = nullptr) {
   static const bool env_tc = []() {
     const char* e = getenv("MMTG_ATTN_TC");
     return !(e && e[0] == '0');
   }();
   const bool use_tc = impl == 2 || (impl == 0 && env_tc);
-  if (use_tc) return attn_fwd_tc(qkv, kmask, out, lse, B, L, NH, st);
+  if (use_tc) return attn_fwd_tc(qkv, kmask, out, lse, B, L, NH, st, drop);
+  MMTG_CHECK_ARG(!drop_on(drop), "attention dropout is implemented by the tcgen05 kernels only (MMTG_ATTN_TC=0 / impl 1 not supported)");
   AttnParams p{};
   p.qkv = qkv; p.kmask = kmask; p.out = out; p.lse = lse;
   p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
@@ -439,15 +441,16 @@ int attn_fwd_impl(const bf16* qkv, const int* kmask, bf16* out, float* lse, int 
 }
 
 int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float* lse, const float* delta,
-                bf16* dqkv, int B, int L, int NH, cudaStream_t st);
+                bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop);
 
 int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
-             cudaStream_t st) {
-  return attn_fwd_impl(qkv, kmask, out, lse, B, L, NH, 0, st);
+             cudaStream_t st, const DropSpec* drop) {
+  return attn_fwd_impl(qkv, kmask, out, lse, B, L, NH, 0, st, drop);
 }
 
 int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
-                  float* delta, bf16* dqkv, int B, int L, int NH, int impl, cudaStream_t st) {
+                  float* delta, bf16* dqkv, int B, int L, int NH, int impl, cudaStream_t st,
+                  const DropSpec* drop = nullptr) {
   // L <= 256: whole-head tcgen05 kernel (attention_tc.cu); longer sequences (config 5),
   // impl == 1 and MMTG_ATTN_BWD_TC=0 use the tiled mma.sync kernels below
   static const bool env_tc = []() {
@@ -464,8 +467,9 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
   MMTG_LAUNCH_OK();
   if (use_tc && L <= 256) {
     count_launch();
-    return attn_bwd_tc(qkv, kmask, dout, lse, delta, dqkv, B, L, NH, st);
+    return attn_bwd_tc(qkv, kmask, dout, lse, delta, dqkv, B, L, NH, st, drop);
   }
+  MMTG_CHECK_ARG(!drop_on(drop), "attention dropout backward needs the tcgen05 kernel (L <= 256, MMTG_ATTN_BWD_TC != 0)");
   dim3 grid(cdiv(L, BQ), B * NH);
   constexpr int BWD_SMEM = 6 * BQ * HD * 2 + 4 * BQ * 4;  // 6 bf16 tiles + 4 x 64 floats
   static bool attr_set = false;
@@ -483,8 +487,8 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
 }
 
 int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
-             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st) {
-  return attn_bwd_impl(qkv, kmask, out, dout, lse, delta, dqkv, B, L, NH, 0, st);
+             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop) {
+  return attn_bwd_impl(qkv, kmask, out, dout, lse, delta, dqkv, B, L, NH, 0, st, drop);
 }
 
 }  // namespace mmtg
@@ -504,6 +508,24 @@ extern "C" int mmtg_attn_bwd_ex(const void* qkv, const int32_t* key_mask, const 
   MMTG_CHECK_ARG(!(impl == 2 && L > 256), "tcgen05 attention backward handles L <= 256");
   return attn_bwd_impl((const bf16*)qkv, key_mask, (const bf16*)out, (const bf16*)dout, lse, delta_ws,
                        (bf16*)dqkv, B, L, n_head, impl, (cudaStream_t)stream);
+}
+
+// dropout variants (tcgen05 kernels): probabilities masked by (seed, site) with keep-rate 1 - p
+extern "C" int mmtg_attn_fwd_drop(const void* qkv, const int32_t* key_mask, void* out, float* lse, int32_t B,
+                                  int32_t L, int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p,
+                                  void* stream) {
+  MMTG_CHECK_ARG(qkv && out && B > 0 && L > 0 && n_head > 0 && p >= 0.f && p < 1.f, "bad attention args");
+  DropSpec d{(const unsigned long long*)seed_dev, site, p, 0};
+  return attn_fwd_impl((const bf16*)qkv, key_mask, (bf16*)out, lse, B, L, n_head, 2, (cudaStream_t)stream, &d);
+}
+extern "C" int mmtg_attn_bwd_drop(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,
+                                  const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L,
+                                  int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p, void* stream) {
+  MMTG_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && L > 0 && L <= 256 && n_head > 0 &&
+                     p >= 0.f && p < 1.f, "bad attention bwd args (dropout backward handles L <= 256)");
+  DropSpec d{(const unsigned long long*)seed_dev, site, p, 0};
+  return attn_bwd_impl((const bf16*)qkv, key_mask, (const bf16*)out, (const bf16*)dout, lse, delta_ws,
+                       (bf16*)dqkv, B, L, n_head, 2, (cudaStream_t)stream, &d);
 }
 
 extern "C" int mmtg_attn_fwd(const void* qkv, const int32_t* key_mask, void* out, float* lse,

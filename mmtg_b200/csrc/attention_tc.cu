@@ -13,7 +13,7 @@
 #include <stdlib.h>
 
 #include "../../include/mmtg_b200.h"
-#include "common.cuh"
+#include "ops.h"
 
 namespace mmtg {
 
@@ -34,6 +34,10 @@ struct AttnTcParams {
   float* lse;        // [B, NH, L]
   int B, L, NH, E;
   float scale;
+  // dropout of the attention probabilities (attn_pdrop): element ((b*NH+h)*L + q) * Lp + key
+  const unsigned long long* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
 };
 
 constexpr int SMEM_Q = 0, SMEM_K = 16384, SMEM_V = 32768, SMEM_P = 49152, SMEM_BAR = 81920;
@@ -139,6 +143,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
     const float sl2 = p.scale * LOG2E;
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = smem + SMEM_P + r * 128;
+    const bool dropping = p.drop_p > 0.f;
+    DropKey dk = {0u, 0u, 0u, 1.f};
+    if (dropping) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
+    // pair index of (this row, key 0): the row sum uses the undropped P, O the dropped one
+    const uint32_t pair_row = (uint32_t)((b * p.NH + h) * p.L + q) * (uint32_t)((p.L + 1) >> 1);
     for (int j = 0; j < nkv; ++j) {
       const float* kmask_j = s_mask + j * TK;  // key padding + sequence end, this block
       ATT_TRACE(20 + 100 * j);
@@ -199,8 +208,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
           float s1 = __uint_as_float(v[i + 1]) * sl2 + kmask_j[kc + 1];
           if (j * TK + kc > q) s0 = -INFINITY;
           if (j * TK + kc + 1 > q) s1 = -INFINITY;
-          const float e0 = exp2f(s0 - m_safe), e1 = exp2f(s1 - m_safe);
+          float e0 = exp2f(s0 - m_safe), e1 = exp2f(s1 - m_safe);
           rs += e0 + e1;
+          if (dropping) {  // the 1/(1-p) factor is applied once, at the end
+            const uint32_t bits = drop_bits(dk, pair_row + (uint32_t)((j * TK + kc) >> 1));
+            e0 = drop_keep_lo(dk, bits) ? e0 : 0.f;
+            e1 = drop_keep_hi(dk, bits) ? e1 : 0.f;
+          }
           __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
         }
@@ -224,7 +238,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
     mbar_wait<17>(bar_o, (uint32_t)((nkv - 1) & 1));
     ATT_TRACE(30);
     tc_fence_after();
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    const float inv = (l_run > 0.f ? 1.f / l_run : 0.f) * dk.inv_keep;
     {
       // tcgen05.ld is .sync.aligned: every lane of the warp loads (rows beyond the sequence
       // included); only the global stores are predicated
@@ -269,7 +283,7 @@ static volatile int* g_attn_trace = nullptr;
 void attn_set_trace(int* host_mapped) { g_attn_trace = host_mapped; }
 
 int attn_fwd_tc(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
-                cudaStream_t st) {
+                cudaStream_t st, const DropSpec* drop) {
   const int E = NH * HD;
   CUtensorMap tm;
   MMTG_CHECK_ARG(L <= 1024, "tcgen05 attention forward handles L <= 1024");
@@ -282,6 +296,9 @@ int attn_fwd_tc(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B,
   AttnTcParams p;
   p.kmask = kmask; p.out = out; p.lse = lse;
   p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
+  p.drop_seed = drop ? drop->seed : nullptr;
+  p.drop_site = drop ? drop->site : 0u;
+  p.drop_p = (drop && drop->seed) ? drop->p : 0.f;
   {
     const char* e = getenv("MMTG_ATTN_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -319,6 +336,9 @@ struct AttnBwdTcParams {
   bf16* dqkv;           // [B*L, 3E]
   int B, L, NH, E;
   float scale;
+  const unsigned long long* drop_seed;  // same mask as the forward (see AttnTcParams)
+  uint32_t drop_site;
+  float drop_p;
 };
 
 // smem map (bytes): 8 operand tiles of 16 KB, then P and dS (32 KB each), then barriers + masks
@@ -437,6 +457,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const float sl2 = p.scale * LOG2E;
     uint8_t* prow = smem + BW_P + r * 128;
     uint8_t* dsrow = smem + BW_DS + r * 128;
+    const bool dropping = p.drop_p > 0.f;
+    DropKey dk = {0u, 0u, 0u, 1.f};
+    if (dropping) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
     // row statistics of both query blocks, fetched once while the operand tiles are in flight
     float lse2_blk[2] = {INFINITY, INFINITY}, dl_blk[2] = {0.f, 0.f};  // +inf -> P = 0 beyond the sequence
 #pragma unroll
@@ -455,6 +478,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const int q = i * 128 + r;
         const float lse2 = i == 0 ? lse2_blk[0] : lse2_blk[1];
         const float dl = i == 0 ? dl_blk[0] : dl_blk[1];
+        const uint32_t pair_row = (uint32_t)((b * p.NH + h) * p.L + q) * (uint32_t)((p.L + 1) >> 1);
         mbar_wait<25>(bar_sdp, (uint32_t)(pair & 1));
         if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
         tc_fence_after();
@@ -468,14 +492,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
           for (int t = 0; t < 32; t += 2) {
             float pe[2], de[2];
+            // with dropout D = keep / (1-p): dV uses P.D, dS = P (D.dP - delta)
+            float dm[2] = {1.f, 1.f};
+            if (dropping) {
+              const uint32_t bits = drop_bits(dk, pair_row + (uint32_t)((j * 128 + c * 32 + t) >> 1));
+              dm[0] = drop_keep_lo(dk, bits) ? dk.inv_keep : 0.f;
+              dm[1] = drop_keep_hi(dk, bits) ? dk.inv_keep : 0.f;
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int kc = c * 32 + t + e;
               const int key = j * 128 + kc;
               float pv = 0.f;
               if (key <= q && s_mask[key] == 0.f) pv = exp2f(__uint_as_float(sv[t + e]) * sl2 - lse2);
-              pe[e] = pv;
-              de[e] = pv * (__uint_as_float(dv[t + e]) - dl);
+              pe[e] = pv * dm[e];
+              de[e] = pv * (__uint_as_float(dv[t + e]) * dm[e] - dl);
             }
             __nv_bfloat162 a = __floats2bfloat162_rn(pe[0], pe[1]), d2 = __floats2bfloat162_rn(de[0], de[1]);
             pp[t >> 1] = *reinterpret_cast<uint32_t*>(&a);
@@ -562,7 +593,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
 // dqkv for L <= 256; `delta` must already hold rowsum(dO * O) (attn_delta_kernel).
 int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float* lse, const float* delta,
-                bf16* dqkv, int B, int L, int NH, cudaStream_t st) {
+                bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop) {
   MMTG_CHECK_ARG(L <= 256, "tcgen05 attention backward handles L <= 256");
   const int E = NH * 64;
   CUtensorMap tm_qkv, tm_do;
@@ -576,6 +607,9 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float
   AttnBwdTcParams p;
   p.kmask = kmask; p.lse = lse; p.delta = delta; p.dqkv = dqkv;
   p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
+  p.drop_seed = drop ? drop->seed : nullptr;
+  p.drop_site = drop ? drop->site : 0u;
+  p.drop_p = (drop && drop->seed) ? drop->p : 0.f;
   attn_bwd_tc_kernel<<<B * NH, 288, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
   MMTG_LAUNCH_OK();
   count_launch();

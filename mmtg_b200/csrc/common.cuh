@@ -369,6 +369,36 @@ __device__ __forceinline__ float dgelu_new_f(float x) {
   float dt = (1.f - t * t) * k0 * (1.f + 3.f * k1 * x2);
   return 0.5f * (1.f + t) + 0.5f * x * dt;
 }
+
+// ---- dropout: counter-based mask, a pure function of (step seed, site, element index) ----
+// The forward and backward kernels of a site regenerate the same mask instead of storing it.
+// One 32-bit hash decides TWO neighbouring elements (16 random bits each); keyed at two points
+// of the mixing function so the streams of different sites are not shifted copies of each other.
+struct DropKey {
+  uint32_t k1, k2, thresh;  // thresh = round(p * 65536); keep iff bits >= thresh
+  float inv_keep;           // 1 / (1 - p)
+};
+__device__ __forceinline__ DropKey drop_key(const unsigned long long* seed, uint32_t site, float p) {
+  DropKey k;
+  const unsigned long long s = seed ? *seed : 0ull;
+  uint32_t x = (uint32_t)s ^ ((uint32_t)(s >> 32) * 0x9E3779B9u) ^ (site * 0x85EBCA6Bu + 0xC2B2AE35u);
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  k.k1 = x;
+  k.k2 = x * 0x9E3779B9u + 0x7F4A7C15u;
+  k.thresh = (uint32_t)(p * 65536.f + 0.5f);
+  k.inv_keep = 1.f / (1.f - p);
+  return k;
+}
+// random bits of elements 2*pair (low half) and 2*pair + 1 (high half)
+__device__ __forceinline__ uint32_t drop_bits(const DropKey& k, uint32_t pair) {
+  uint32_t x = pair ^ k.k1;
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= (x >> 15) ^ k.k2; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool drop_keep_lo(const DropKey& k, uint32_t bits) { return (bits & 0xffffu) >= k.thresh; }
+__device__ __forceinline__ bool drop_keep_hi(const DropKey& k, uint32_t bits) { return (bits >> 16) >= k.thresh; }
 #endif  // __CUDACC__
 
 }  // namespace mmtg

@@ -7,7 +7,7 @@
 // per-token embedding loops of GPT2_Decoder.forward (src/model.py:253-268) and the ATen
 // reductions autograd uses for bias gradients.
 #include "../../include/mmtg_b200.h"
-#include "common.cuh"
+#include "ops.h"
 
 namespace mmtg {
 
@@ -79,7 +79,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, float* __restrict__ dx, int accumulate_dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ dx16,
-              float* __restrict__ dx_colsum, int M) {
+              float* __restrict__ dx_colsum, int M, const unsigned long long* __restrict__ drop_seed,
+              uint32_t drop_site, float drop_p, int drop_dx32) {
   // Two passes over a tile of TR rows (second pass re-reads from L1/L2):
   //   1. warp per row: m1 = mean(g), m2 = mean(g * xhat), g = dy * gamma   -> shared memory
   //   2. thread per column pair: dx for every row of the tile, column sums in 6 registers
@@ -90,6 +91,12 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
   const int c = threadIdx.x * 2;
   const float2 gam2 = *reinterpret_cast<const float2*>(gamma + c);
   float2 adg = make_float2(0.f, 0.f), adb = adg, acs = adg;
+  // dx16 / dx_colsum feed the backward of a residual branch whose forward output went through
+  // dropout: they carry dx * mask / (1 - p); the fp32 dx (residual stream) stays unmasked unless
+  // drop_dx32 (embedding dropout: nothing below needs the unmasked gradient)
+  const bool dropping = drop_p > 0.f;
+  DropKey dk = {0u, 0u, 0u, 1.f};
+  if (dropping) dk = drop_key(drop_seed, drop_site, drop_p);
   // each block owns ONE contiguous row range (balanced single wave), walked in tiles of TR rows
   const int rows_per_block = cdiv(M, (int)gridDim.x);
   const int r_begin = blockIdx.x * rows_per_block, r_end = min(M, r_begin + rows_per_block);
@@ -147,11 +154,17 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
         o.x += old.x;
         o.y += old.y;
       }
-      *reinterpret_cast<float2*>(dx + off) = o;
-      if (dx16) *reinterpret_cast<__nv_bfloat162*>(dx16 + off) = __floats2bfloat162_rn(o.x, o.y);
+      float2 om = o;
+      if (dropping) {
+        const uint32_t bits = drop_bits(dk, (uint32_t)(off >> 1));
+        om.x = drop_keep_lo(dk, bits) ? o.x * dk.inv_keep : 0.f;
+        om.y = drop_keep_hi(dk, bits) ? o.y * dk.inv_keep : 0.f;
+      }
+      *reinterpret_cast<float2*>(dx + off) = drop_dx32 ? om : o;
+      if (dx16) *reinterpret_cast<__nv_bfloat162*>(dx16 + off) = __floats2bfloat162_rn(om.x, om.y);
       adg.x += dyv.x * xh0; adg.y += dyv.y * xh1;
       adb.x += dyv.x; adb.y += dyv.y;
-      acs.x += o.x; acs.y += o.y;
+      acs.x += om.x; acs.y += om.y;
     }
     __syncthreads();
   }
@@ -349,12 +362,16 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y
 
 int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd,
                   const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
-                  bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st) {
+                  bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st, const DropSpec* drop) {
+  const unsigned long long* dseed = drop ? drop->seed : nullptr;
+  const uint32_t dsite = drop ? drop->site : 0u;
+  const float dp = (drop && drop->seed) ? drop->p : 0.f;
+  const int ddx32 = drop ? drop->mask_dx32 : 0;
   MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
   // 3 blocks of E/2 threads are resident per SM (56 registers): one balanced wave
   const int blocks = max(1, min(M, num_sms() * 3));
   ProfScope prof(2, 0, (double)M * E * (4 + (dy_bf16 ? 2 : 4) + 4 + (accumulate_dx ? 4 : 0) + (dx16 ? 2 : 0)), st);
-#define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, EE / 2, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, dx16, dx_colsum, M)
+#define LNB(EE, BF) ln_bwd_kernel<EE, BF><<<blocks, EE / 2, 0, st>>>(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, dx16, dx_colsum, M, dseed, dsite, dp, ddx32)
   if (E == 768) { if (dy_bf16) LNB(768, true); else LNB(768, false); }
   else { if (dy_bf16) LNB(512, true); else LNB(512, false); }
 #undef LNB
@@ -464,4 +481,47 @@ extern "C" int mmtg_embed_bwd(const void* dE_bf16, void* dctx_bf16, float* dctx_
                               int32_t T, int32_t S, int32_t two_sent, int32_t D, void* stream) {
   MMTG_CHECK_ARG(dE_bf16 && (dctx_bf16 || dctx_f32), "bad embed bwd args");
   return embed_bwd((const bf16*)dE_bf16, (bf16*)dctx_bf16, dctx_f32, B, P, T, S, two_sent, D, (cudaStream_t)stream);
+}
+
+// ---- dropout helpers (tests / step seed) ----
+namespace mmtg {
+namespace {
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(const unsigned long long* __restrict__ seed, uint32_t site, float p, long long n,
+                    uint8_t* __restrict__ keep) {
+  const DropKey dk = drop_key(seed, site, p);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr * 2 < n; pr += stride) {
+    const uint32_t bits = drop_bits(dk, (uint32_t)pr);
+    keep[pr * 2] = drop_keep_lo(dk, bits) ? 1 : 0;
+    if (pr * 2 + 1 < n) keep[pr * 2 + 1] = drop_keep_hi(dk, bits) ? 1 : 0;
+  }
+}
+__global__ void seed_next_kernel(unsigned long long* seed) {
+  // splitmix64 step: consecutive steps get unrelated keys
+  unsigned long long z = (*seed += 0x9E3779B97F4A7C15ull);
+  (void)z;
+}
+}  // namespace
+}  // namespace mmtg
+
+extern "C" int mmtg_dropout_mask(const uint64_t* seed_dev, uint32_t site, float p, int64_t n, uint8_t* keep_out,
+                                 void* stream) {
+  using namespace mmtg;
+  MMTG_CHECK_ARG(seed_dev && keep_out && n > 0 && p >= 0.f && p < 1.f, "bad dropout_mask args");
+  const int blocks = (int)((n / 2 + 255) / 256 < 4096 ? (n / 2 + 255) / 256 + 1 : 4096);
+  dropout_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)seed_dev, site, p,
+                                                                (long long)n, keep_out);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+extern "C" int mmtg_dropout_next_seed(uint64_t* seed_dev, void* stream) {
+  using namespace mmtg;
+  MMTG_CHECK_ARG(seed_dev, "null seed");
+  seed_next_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)seed_dev);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
 }

@@ -206,8 +206,23 @@ struct Gemm {
   Gemm& colsum(float* c) { a.colsum = c; return *this; }
   Gemm& accumulate(int split = 1) { a.accumulate = 1; a.split_k = split; return *this; }
   Gemm& lse(float* p, int bn) { a.lse_partial = p; a.block_n = bn; return *this; }
+  Gemm& dropout(const DropSpec& d) {
+    if (d.seed && d.p > 0.f) { a.drop_seed = (const uint64_t*)d.seed; a.drop_site = d.site; a.drop_p = d.p; }
+    return *this;
+  }
   int run(cudaStream_t st) { return mmtg_gemm_bf16(&a, (void*)st); }
 };
+
+// dropout sites of the decoder (include/mmtg_b200.h): block l -> 4l + {0 attn probs, 1 attn
+// c_proj, 2 mlp c_proj}; MMTG_DROP_SITE_EMBD for the embedding sum
+inline DropSpec drop_spec(const mmtg_model* m, uint32_t site, float p, int mask_dx32 = 0) {
+  DropSpec d;
+  d.seed = (p > 0.f) ? (const unsigned long long*)m->drop_seed : nullptr;
+  d.site = site;
+  d.p = d.seed ? p : 0.f;
+  d.mask_dx32 = mask_dx32;
+  return d;
+}
 
 // wgrad: dW[rows, cols] += X^T Y with X [K, rows] and Y [K, cols] row-major activations.
 // Output tiles are few (dW is at most 768 x 3072), so the reduction dimension (the tokens) is
@@ -355,6 +370,7 @@ extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void
     g.out_f32(w.h0, E).bias(P + o.proj2_b);
     g.a.rowtab0 = P + o.wpe; g.a.ldt0 = E; g.a.rowmod0 = d.L;
     g.a.rowtab1 = P + o.wte; g.a.ldt1 = E; g.a.rowidx1 = b->type_ids;
+    g.dropout(drop_spec(m, MMTG_DROP_SITE_EMBD, m->p_embd));  // embd_pdrop (HF modeling_gpt2.py:612)
     MMTG_TRY(g.run(st));
   }
   // ---------------- GPT-2 blocks (HF modeling_gpt2.py:262-309) ----------------
@@ -364,14 +380,16 @@ extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void
     MMTG_TRY(layernorm_fwd(L.h_in, P + lo.ln1_w, P + lo.ln1_b, L.x1, nullptr, L.mean1, L.rstd1, M, E, eps, st));
     MMTG_TRY(Gemm(L.x1, E, false, W + lo.attn_w, 3 * E, true, M, 3 * E, E)
                  .out_bf16(L.qkv, 3 * E).bias(P + lo.attn_b).run(st));
-    MMTG_TRY(attn_fwd(L.qkv, b->attn_mask, L.att, L.lse, B, d.L, d.NH, st));
+    const DropSpec d_att = drop_spec(m, 4u * l, m->p_attn), d_r1 = drop_spec(m, 4u * l + 1, m->p_resid),
+                   d_r2 = drop_spec(m, 4u * l + 2, m->p_resid);
+    MMTG_TRY(attn_fwd(L.qkv, b->attn_mask, L.att, L.lse, B, d.L, d.NH, st, &d_att));
     MMTG_TRY(Gemm(L.att, E, false, W + lo.proj_w, E, true, M, E, E)
-                 .out_f32(L.h_mid, E).bias(P + lo.proj_b).residual(L.h_in, E).run(st));
+                 .out_f32(L.h_mid, E).bias(P + lo.proj_b).residual(L.h_in, E).dropout(d_r1).run(st));
     MMTG_TRY(layernorm_fwd(L.h_mid, P + lo.ln2_w, P + lo.ln2_b, L.x2, nullptr, L.mean2, L.rstd2, M, E, eps, st));
     MMTG_TRY(Gemm(L.x2, E, false, W + lo.fc_w, 4 * E, true, M, 4 * E, E)
                  .out_bf16(L.a, 4 * E).out2_deriv(L.u, 4 * E).bias(P + lo.fc_b).act(MMTG_ACT_GELU_NEW).run(st));
     MMTG_TRY(Gemm(L.a, 4 * E, false, W + lo.proj2_w, E, true, M, E, 4 * E)
-                 .out_f32(L.h_out, E).bias(P + lo.proj2_b).residual(L.h_mid, E).run(st));
+                 .out_f32(L.h_out, E).bias(P + lo.proj2_b).residual(L.h_mid, E).dropout(d_r2).run(st));
   }
   // ---------------- ln_f + tied lm_head + HF loss ----------------
   const float* h_last = w.layer[d.NL - 1].h_out;
@@ -409,8 +427,10 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       // dwte += dlogits^T · xf
       MMTG_TRY(wgrad(w.dlogits16, d.Vp, w.xf, E, G + o.wte, E, d.V, E, M, st));
       // also emits g16 = bf16(dh) and the mlp c_proj bias gradient of the top block
+      // (masked by the top block's mlp resid dropout: g16 is the gradient of the c_proj OUTPUT)
+      const DropSpec dr = drop_spec(m, 4u * (d.NL - 1) + 2, m->p_resid);
       MMTG_TRY(layernorm_bwd(w.dx, 1, w.layer[d.NL - 1].h_out, w.meanf, w.rstdf, P + o.lnf_w, w.dh, 0,
-                             G + o.lnf_w, G + o.lnf_b, w.g16, G + o.layer[d.NL - 1].proj2_b, M, E, st));
+                             G + o.lnf_w, G + o.lnf_b, w.g16, G + o.layer[d.NL - 1].proj2_b, M, E, st, &dr));
     } else if (stage <= d.NL) {
       const int l = d.NL - stage;
       const LayerWs& L = w.layer[l];
@@ -421,19 +441,25 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       MMTG_TRY(wgrad(L.a, 4 * E, w.g16, E, G + lo.proj2_w, E, 4 * E, E, M, st));
       MMTG_TRY(Gemm(w.du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(w.dx, E).run(st));
       MMTG_TRY(wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, st));
+      const DropSpec d_att = drop_spec(m, 4u * l, m->p_attn), d_r1 = drop_spec(m, 4u * l + 1, m->p_resid);
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_mid, L.mean2, L.rstd2, P + lo.ln2_w, w.dh, 1, G + lo.ln2_w,
-                             G + lo.ln2_b, w.g16, G + lo.proj_b, M, E, st));
+                             G + lo.ln2_b, w.g16, G + lo.proj_b, M, E, st, &d_r1));
       // ---- attention ----
       MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(w.datt, E).run(st));
       MMTG_TRY(wgrad(L.att, E, w.g16, E, G + lo.proj_w, E, E, E, M, st));
-      MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, w.datt, L.lse, w.delta, w.dqkv, B, d.L, d.NH, st));
+      MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, w.datt, L.lse, w.delta, w.dqkv, B, d.L, d.NH, st, &d_att));
       MMTG_TRY(colsum(w.dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, st));
       MMTG_TRY(Gemm(w.dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(w.dx, E).run(st));
       MMTG_TRY(wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, st));
       // dh is now the gradient of this block's input: its bf16 copy / column sums feed the block
       // below (mlp c_proj bias) or, for block 0, the projector (projector_layer2 bias)
+      // (masked by the dropout that produced this block's input: the mlp resid dropout of the
+      // block below, or the embedding dropout — there the fp32 dh is masked too)
+      const DropSpec d_in = l > 0 ? drop_spec(m, 4u * (l - 1) + 2, m->p_resid)
+                                  : drop_spec(m, MMTG_DROP_SITE_EMBD, m->p_embd, 1);
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_in, L.mean1, L.rstd1, P + lo.ln1_w, w.dh, 1, G + lo.ln1_w,
-                             G + lo.ln1_b, w.g16, l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, st));
+                             G + lo.ln1_b, w.g16, l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, st,
+                             &d_in));
     } else {
       // ---------------- embeddings + projector ----------------
       MMTG_TRY(posadd_bwd(w.dh, G + o.wpe, B, d.L, E, st));

@@ -57,6 +57,9 @@ struct GemmParams {
   int vec4;
   int dact_tanh_out;
   int out2_mode;
+  const unsigned long long* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
 };
 
 // TWO = cta_group::2: the pair's 256 x BN tile is ONE MMA; each CTA stages its own 128 A rows and
@@ -83,7 +86,7 @@ struct GemmCfg {
 // epilogue feature bits (compile-time mask EPI)
 enum : uint32_t {
   F_OUT2 = 1, F_ACT = 2, F_DACT = 4, F_RES = 8, F_ROWTAB = 16, F_COLSUM = 32, F_ATOMIC = 64,
-  F_LSE = 128, F_SCALAR = 256
+  F_LSE = 128, F_SCALAR = 256, F_DROP = 512
 };
 
 template <int BN, uint32_t EPI, bool TWO>
@@ -277,6 +280,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int rs = lane >> 3, cg = lane & 7;  // vector mapping: row sub-index, 4-column group
     int acc = 0;
     uint32_t acc_ph = 0;
+    DropKey dk = {0u, 0u, 0u, 1.f};
+    if constexpr (EPI & F_DROP) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
     for (int w = cluster_id; w < total; w += nclusters) {
       const int tile = w / p.splits;
       const int n_t = tile / p.num_mp, m_t = (tile - n_t * p.num_mp) * 2 + (int)crank;
@@ -435,6 +440,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
               }
             }
           }
+          // inverted dropout of the value: before the residual add (resid_pdrop) ...
+          auto apply_drop = [&]() {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const uint32_t pair = (uint32_t)(((row0 + it * 4) * p.N + col) >> 1);
+              const uint32_t b0 = drop_bits(dk, pair), b1 = drop_bits(dk, pair + 1);
+              v[it][0] = drop_keep_lo(dk, b0) ? v[it][0] * dk.inv_keep : 0.f;
+              v[it][1] = drop_keep_hi(dk, b0) ? v[it][1] * dk.inv_keep : 0.f;
+              v[it][2] = drop_keep_lo(dk, b1) ? v[it][2] * dk.inv_keep : 0.f;
+              v[it][3] = drop_keep_hi(dk, b1) ? v[it][3] * dk.inv_keep : 0.f;
+            }
+          };
+          if constexpr ((EPI & F_DROP) && (EPI & F_RES)) {
+            if (p.drop_p > 0.f) apply_drop();
+          }
           if constexpr (EPI & F_RES) {
             if (p.residual) {
 #pragma unroll
@@ -463,6 +483,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                   v[it][0] += t.x; v[it][1] += t.y; v[it][2] += t.z; v[it][3] += t.w;
                 }
             }
+          }
+          // ... or of the embedding sum, after the row-table adds (embd_pdrop)
+          if constexpr ((EPI & F_DROP) && !(EPI & F_RES)) {
+            if (p.drop_p > 0.f) apply_drop();
           }
           if constexpr (EPI & F_COLSUM) {
             if (p.colsum) {
@@ -762,6 +786,8 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   p.colsum = a->colsum;
   p.lse_partial = a->lse_partial;
   p.dact_tanh_out = a->dact_tanh_out;
+  p.drop_seed = (const unsigned long long*)a->drop_seed; p.drop_site = a->drop_site;
+  p.drop_p = a->drop_seed ? a->drop_p : 0.f;
   p.out2_mode = a->out2_mode;
   MMTG_CHECK_ARG(!(p.lse_partial && p.splits > 1), "lse_partial is incompatible with split_k");
   {
@@ -795,6 +821,11 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   if (p.atomic) need |= F_ATOMIC;
   if (p.lse_partial) need |= F_LSE;
   if (!p.vec4) need |= F_SCALAR;
+  if (p.drop_p > 0.f) {
+    MMTG_CHECK_ARG(p.drop_p < 1.f && p.vec4 && a->N % 4 == 0 && !p.atomic && (p.residual || p.rowtab0 || p.rowtab1),
+                   "dropout epilogue: needs p < 1, N %% 4 == 0, aligned operands, and a residual or row-table epilogue");
+    need |= F_DROP;
+  }
   static const bool two_sm = []() {  // MMTG_GEMM_2SM=0 selects the 1-SM (multicast) kernel
     const char* e = getenv("MMTG_GEMM_2SM");
     return !(e && e[0] == '0');
@@ -811,9 +842,11 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   MMTG_TRY_EPI(0u)
   MMTG_TRY_EPI(F_ACT | F_OUT2)
   MMTG_TRY_EPI(F_RES)
+  MMTG_TRY_EPI(F_RES | F_DROP)
   MMTG_TRY_EPI(F_DACT | F_COLSUM)
   MMTG_TRY_EPI(F_ATOMIC)
   MMTG_TRY_EPI(F_ROWTAB)
+  MMTG_TRY_EPI(F_ROWTAB | F_DROP)
   MMTG_TRY_EPI(F_SCALAR | F_LSE)
   MMTG_TRY_EPI(F_SCALAR | F_ACT | F_RES | F_COLSUM | F_ATOMIC)
   MMTG_TRY_EPI(F_OUT2 | F_ACT | F_DACT | F_RES | F_ROWTAB | F_COLSUM | F_ATOMIC | F_LSE)

@@ -4,12 +4,20 @@
 
 namespace mmtg {
 
+// dropout of one site (common.cuh: drop_key / drop_bits); seed == nullptr or p == 0: off
+struct DropSpec {
+  const unsigned long long* seed;
+  uint32_t site;
+  float p;
+  int mask_dx32;  // layernorm_bwd: also mask the fp32 dx (embedding dropout)
+};
+
 // elementwise.cu
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y16, float* y32,
                   float* mean, float* rstd, int M, int E, float eps, cudaStream_t st);
 int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd,
                   const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
-                  bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st);
+                  bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st, const DropSpec* drop = nullptr);
 int cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
 int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc, float* out, int M,
            int N, cudaStream_t st);
@@ -23,9 +31,9 @@ int dlogits_f32_to_bf16(const float* src, bf16* dst, int M, int V, int Vp, cudaS
 
 // attention.cu
 int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
-             cudaStream_t st);
+             cudaStream_t st, const DropSpec* drop = nullptr);
 int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
-             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st);
+             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop = nullptr);
 
 // loss.cu
 int lse_rows(const float* logits, long long ld, float* lse, int M, int V, cudaStream_t st);

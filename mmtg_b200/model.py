@@ -58,7 +58,9 @@ class ParamOffsets(C.Structure):
 
 class Model(C.Structure):
     _fields_ = [("dims", Dims), ("off", ParamOffsets), ("params", C.c_void_p),
-                ("params_bf16", C.c_void_p), ("grads", C.c_void_p), ("token_table", C.c_void_p)]
+                ("params_bf16", C.c_void_p), ("grads", C.c_void_p), ("token_table", C.c_void_p),
+                ("drop_seed", C.c_void_p), ("p_embd", C.c_float), ("p_resid", C.c_float),
+                ("p_attn", C.c_float), ("_pad_drop", C.c_int32)]
 
 
 class Batch(C.Structure):
@@ -224,6 +226,13 @@ class MMTG(nn.Module):
         self._serial = 0
         self._anchor = None
         self.grad_sync = None   # optional parallel.GradSync
+        g = self.decoder.config
+        # GPT-2 dropout, live while `self.training and self.train_flag` (nn.Module.eval() or
+        # set_dropout(0, 0, 0) turn it off: parity with the reference is defined at p = 0)
+        self._drop_p = (float(g.get("embd_pdrop", 0.1)), float(g.get("resid_pdrop", 0.1)),
+                        float(g.get("attn_pdrop", 0.1)))
+        self._drop_seed = None  # device int64: masks are functions of (seed, site, element)
+        self._drop_seed_init = 0x5EED
         self._build_layout()
         self.reset_parameters()
         if train_flag and os.path.isfile(model_cfgs.get("GPT2_PATH", "")):
@@ -542,12 +551,37 @@ class MMTG(nn.Module):
         _run_backward(step, self._alpha_buf)
         return total, loss, kl
 
-    def _c_model(self, d, device):
+    def set_dropout(self, embd=None, resid=None, attn=None):
+        """Override the GPT-2 dropout probabilities (HF embd_pdrop / resid_pdrop / attn_pdrop)."""
+        e, r, a = self._drop_p
+        self._drop_p = (e if embd is None else float(embd), r if resid is None else float(resid),
+                        a if attn is None else float(attn))
+        return self
+
+    def set_dropout_seed(self, seed):
+        """Seed of the counter-based dropout masks; every training forward advances it."""
+        self._drop_seed_init = int(seed) & 0x7FFFFFFFFFFFFFFF
+        if self._drop_seed is not None:
+            self._drop_seed.fill_(self._drop_seed_init)
+        return self
+
+    def dropout_active(self):
+        return bool(self.training and self.train_flag and any(p > 0 for p in self._drop_p))
+
+    def _seed_tensor(self, device):
+        if self._drop_seed is None or self._drop_seed.device != device:
+            self._drop_seed = torch.full((1,), self._drop_seed_init, dtype=torch.int64, device=device)
+        return self._drop_seed
+
+    def _c_model(self, d, device, train=False):
         m = Model()
         m.dims, m.off = d, self._offsets
         P, W16, G = self._flat
         m.params, m.params_bf16, m.grads = P.data_ptr(), W16.data_ptr(), G.data_ptr()
         m.token_table = self._table(device).data_ptr()
+        if train and self.dropout_active():
+            m.drop_seed = self._seed_tensor(device).data_ptr()
+            m.p_embd, m.p_resid, m.p_attn = self._drop_p
         return m
 
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -597,8 +631,11 @@ def _c_batch(step):
 def _run_forward(step):
     mdl = step.model
     device = step.logits.device
-    m, b = mdl._c_model(step.dims, device), _c_batch(step)
+    m, b = mdl._c_model(step.dims, device, train=True), _c_batch(step)
     step.cm, step.cb = m, b
+    if m.drop_seed:  # fresh masks for this step; backward regenerates them from the same seed
+        _lib.check(_lib.lib().mmtg_dropout_next_seed(C.c_void_p(m.drop_seed), C.c_void_p(_lib.stream_ptr())),
+                   "mmtg_dropout_next_seed")
     rc = _lib.lib().mmtg_train_forward(C.byref(m), C.byref(b), C.c_void_p(step.ws.data_ptr()),
                                        C.c_int64(step.ws.numel()), C.c_void_p(step.logits.data_ptr()),
                                        C.c_void_p(step.scalars.data_ptr()), 1, C.c_void_p(_lib.stream_ptr()))

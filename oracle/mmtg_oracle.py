@@ -132,15 +132,27 @@ def gelu_new(x):
     return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
 
 
+def _drop(x, keep, p):
+    """Inverted dropout with an INJECTED keep mask (torch.nn.functional.dropout's arithmetic)."""
+    return x * keep.to(x.dtype) / (1.0 - p)
+
+
 def gpt2_forward(sd, inputs_embeds, token_type_ids, attention_mask, n_layer=12, n_head=12,
-                 prefix="decoder.gpt2.transformer."):
-    """HF GPT2Model.forward + lm_head (modeling_gpt2.py:522-636, 703-706), eval mode (no dropout).
-    Conv1D: y = x @ W + b with W stored [in, out] (pytorch_utils.py:97-123)."""
+                 prefix="decoder.gpt2.transformer.", dropout=None):
+    """HF GPT2Model.forward + lm_head (modeling_gpt2.py:522-636, 703-706).
+    Conv1D: y = x @ W + b with W stored [in, out] (pytorch_utils.py:97-123).
+    dropout=None: eval mode. Otherwise the train-mode dropouts (embd :612, attention
+    probabilities :67, resid after both c_proj :150/:259) with injected keep masks:
+    {"p": (embd, resid, attn), "embd": [B,L,E], "attn": [n_layer x [B,NH,L,L]],
+     "resid1": [n_layer x [B,L,E]], "resid2": [n_layer x [B,L,E]]}."""
     B, L, E = inputs_embeds.shape
     dh = E // n_head
     pos = torch.arange(L, device=inputs_embeds.device)
     h = inputs_embeds + sd[prefix + "wpe.weight"][pos]
     h = h + sd[prefix + "wte.weight"][token_type_ids]  # type ids index the WORD table
+    if dropout is not None:
+        pe, pr, pa = dropout["p"]
+        h = _drop(h, dropout["embd"], pe)
     causal = torch.ones(L, L, dtype=torch.bool, device=h.device).tril()
     keep = causal.view(1, 1, L, L) & (attention_mask.view(B, 1, 1, L) != 0)
     for l in range(n_layer):
@@ -153,12 +165,21 @@ def gpt2_forward(sd, inputs_embeds, token_type_ids, attention_mask, n_layer=12, 
         v = v.view(B, L, n_head, dh).transpose(1, 2)
         s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
         s = s.masked_fill(~keep, float("-inf"))
-        a = torch.softmax(s, -1) @ v
+        w = torch.softmax(s, -1)
+        if dropout is not None:
+            w = _drop(w, dropout["attn"][l], pa)
+        a = w @ v
         a = a.transpose(1, 2).reshape(B, L, E)
-        h = h + a @ sd[p + "attn.c_proj.weight"] + sd[p + "attn.c_proj.bias"]
+        o = a @ sd[p + "attn.c_proj.weight"] + sd[p + "attn.c_proj.bias"]
+        if dropout is not None:
+            o = _drop(o, dropout["resid1"][l], pr)
+        h = h + o
         x = F.layer_norm(h, (E,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], LN_EPS)
         u = gelu_new(x @ sd[p + "mlp.c_fc.weight"] + sd[p + "mlp.c_fc.bias"])
-        h = h + u @ sd[p + "mlp.c_proj.weight"] + sd[p + "mlp.c_proj.bias"]
+        o = u @ sd[p + "mlp.c_proj.weight"] + sd[p + "mlp.c_proj.bias"]
+        if dropout is not None:
+            o = _drop(o, dropout["resid2"][l], pr)
+        h = h + o
     h = F.layer_norm(h, (E,), sd[prefix + "ln_f.weight"], sd[prefix + "ln_f.bias"], LN_EPS)
     return h @ sd[prefix + "wte.weight"].t()  # tied lm_head, no bias
 
@@ -202,8 +223,9 @@ def inference_type_ids_and_mask(input_ids_row0, tpw_type_ids, tpw_att_mask, sent
             torch.cat([tpw_att_mask.long(), mask.to(tpw_att_mask.device)], 1))
 
 
-def mmtg_forward(sd, table, batch, data_config, train_flag=True):
-    """MMTG.forward, src/model.py:356-400 -> (hf_loss, kl, logits [B, P+T, V])."""
+def mmtg_forward(sd, table, batch, data_config, train_flag=True, dropout=None):
+    """MMTG.forward, src/model.py:356-400 -> (hf_loss, kl, logits [B, P+T, V]).
+    `dropout`: injected GPT-2 keep masks (see gpt2_forward); None = eval mode."""
     ctx, kl = fused_context(sd, batch)
     input_ids, topic_ids = batch["targets"].long(), batch["topic_ids"].long()
     sent_len = data_config["max_sent_length"] + 2
@@ -220,7 +242,7 @@ def mmtg_forward(sd, table, batch, data_config, train_flag=True):
         labels = torch.zeros(emb.shape[0], emb.shape[1], dtype=torch.long)
     h1 = torch.tanh(emb @ sd["decoder.projector_layer1.weight"].t() + sd["decoder.projector_layer1.bias"])
     x = h1 @ sd["decoder.projector_layer2.weight"].t() + sd["decoder.projector_layer2.bias"]
-    logits = gpt2_forward(sd, x, types, mask)
+    logits = gpt2_forward(sd, x, types, mask, dropout=dropout)
     return hf_causal_lm_loss(logits, labels), kl, logits
 
 

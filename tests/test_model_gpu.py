@@ -23,6 +23,7 @@ def world(cuda):
     table = synth.make_token_table()
     sd = synth.make_state_dict(0)
     model = MMTG(model_cfgs, data_config(), 13317, train_flag=True, token_table=table)
+    model.set_dropout(0.0, 0.0, 0.0)  # parity with the reference is defined at p = 0 (test_dropout_gpu.py covers p > 0)
     model.load_state_dict(sd)
     model.to(cuda)
     return model, sd, table
@@ -178,6 +179,7 @@ def test_extended_lyrics_length_forward_backward(cuda, max_sent_length):
     table = synth.make_token_table()
     sd = synth.make_state_dict(1, gpt2_cfg=g2)
     model = MMTG(model_cfgs, dc, 13317, train_flag=True, token_table=table, gpt2_config=g2)
+    model.set_dropout(0.0, 0.0, 0.0)
     model.load_state_dict(sd)
     model.to(cuda)
     host = synth.batch_to_torch(synth.make_batch(2, seed=11, data_config=dc, ratings=np.array([1, 5])))
