@@ -48,35 +48,70 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons DURING the timed region: NVML polled every 50 ms (nvidia-smi
+    subprocesses are too slow when 8 ranks sample at once), nvidia-smi as the fallback."""
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                ("sw_power_cap", 0x4))
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            self.rows.append((float(sm), float(mx), {name for name, bit in self._REASONS if mask & bit}))
+            return
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout
+        c = [x.strip() for x in out.strip().split(",")]
+        if len(c) >= 6 and c[0].replace(".", "").isdigit():
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((float(c[0]), float(c[1]), {nm for nm, v in zip(names, c[2:6]) if v.lower().startswith("active")}))
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                self._sample()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05 if self.nvml is not None else 0.2)
 
     def summary(self):
         self._stop_evt.set()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
         reasons = set()
         for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+            reasons |= r[2]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_train_step_time(batch_size, reps, threads):
@@ -209,11 +244,13 @@ def main():
     l0 = lib.mmtg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()  # ncu --profile-from-start off: capture exactly the timed steps
     e0.record()
     for _ in range(K):
         step(resident)
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     launches = int(lib.mmtg_launch_count() - l0)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:

@@ -316,7 +316,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) +
                           (uint32_t)(acc * BN + half * (BN / 2) + c * 32), r);
-        // issue this chunk's global operand loads while the TMEM load is in flight
+        // issue this chunk's global operand loads while the TMEM load is in flight (fetching
+        // them one chunk ahead was measured SLOWER: +32..48 live registers spill at the 168
+        // cap and the extra moves outweigh the hidden latency)
         const int col = col0 + cg * 4;
         const bool colok = col < p.N;  // N % 4 == 0 in vec mode
         bool ok[8];
@@ -391,26 +393,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             v[it][0] = t.x + b4.x; v[it][1] = t.y + b4.y;
             v[it][2] = t.z + b4.z; v[it][3] = t.w + b4.w;
           }
+          bool act_done = false;
           if constexpr (EPI & F_OUT2) {
             if (p.out2) {
               const bool deriv = p.out2_mode == 1 && p.act == MMTG_ACT_GELU_NEW;
+              if (deriv) {
+                // gelu_new and its derivative from ONE tanh (c_fc forward: the activation goes to
+                // the mlp c_proj, the derivative is kept for the backward multiply)
+                act_done = true;
 #pragma unroll
-              for (int it = 0; it < 8; ++it)
-                if (ok[it]) {
-                  float w0 = v[it][0], w1 = v[it][1], w2 = v[it][2], w3 = v[it][3];
-                  if (deriv) {
-                    w0 = dgelu_new_fast(w0); w1 = dgelu_new_fast(w1);
-                    w2 = dgelu_new_fast(w2); w3 = dgelu_new_fast(w3);
+                for (int it = 0; it < 8; ++it) {
+                  float dv[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) gelu_new_both(v[it][e], v[it][e], dv[e]);
+                  if (ok[it]) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(dv[0], dv[1]);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(dv[2], dv[3]);
+                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    *reinterpret_cast<uint2*>(p.out2 + (row0 + it * 4) * p.ldo2 + col) = pk;
                   }
-                  __nv_bfloat162 lo = __floats2bfloat162_rn(w0, w1);
-                  __nv_bfloat162 hi = __floats2bfloat162_rn(w2, w3);
-                  uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                  *reinterpret_cast<uint2*>(p.out2 + (row0 + it * 4) * p.ldo2 + col) = pk;
                 }
+              } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  if (ok[it]) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[it][0], v[it][1]);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(v[it][2], v[it][3]);
+                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    *reinterpret_cast<uint2*>(p.out2 + (row0 + it * 4) * p.ldo2 + col) = pk;
+                  }
+              }
             }
           }
           if constexpr (EPI & F_ACT) {
-            if (p.act == MMTG_ACT_TANH) {
+            if (act_done) {
+            } else if (p.act == MMTG_ACT_TANH) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
 #pragma unroll

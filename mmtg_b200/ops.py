@@ -18,7 +18,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          a_mn_major: bool = False, b_mn_major: bool = False, bias=None, act: int = ACT_NONE,
          out2=None, residual=None, dgelu_src=None, rowtab0=None, rowidx0=None, rowmod0: int = 0,
          rowtab1=None, rowidx1=None, colsum=None, lse_partial=None, accumulate: bool = False,
-         split_k: int = 1, block_n: int = 0, skinny: bool = False) -> torch.Tensor:
+         split_k: int = 1, block_n: int = 0, skinny: bool = False, out2_mode: int = 0, dact_mode: int = 0,
+         drop=None) -> torch.Tensor:
     """out = epilogue(A · Bᵀ) on the tcgen05 GEMM (see include/mmtg_b200.h: mmtg_gemm_bf16)."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert out.dtype in (torch.float32, torch.bfloat16)
@@ -60,6 +61,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     if lse_partial is not None:
         assert lse_partial.dtype == torch.float32
         a.lse_partial = lse_partial.data_ptr()
+    a.out2_mode, a.dact_tanh_out = out2_mode, dact_mode
+    if drop is not None:  # (device int64 seed tensor, site, p)
+        a.drop_seed, a.drop_site, a.drop_p = drop[0].data_ptr(), int(drop[1]), float(drop[2])
     fn = _lib.lib().mmtg_skinny_gemm_bf16 if skinny else _lib.lib().mmtg_gemm_bf16
     _lib.check(fn(C.byref(a), C.c_void_p(_lib.stream_ptr())), "mmtg_gemm_bf16")
     return out

@@ -30,12 +30,16 @@ for name, kw in (("greedy", dict(temperature=1.0, top_k=1, top_p=0.0, repitition
     for graph in (True, False):
         ts = []
         for rep in range(3):
+            if rep == 2 and name == "greedy" and not graph:
+                torch.cuda.profiler.start()  # ncu --profile-from-start off: one eager generation
             torch.cuda.synchronize()
             l0 = _lib.launch_count()
             t0 = time.perf_counter()
             rows = sample_sequence_batch(model, starts, LENGTH, device="cuda", use_cuda_graph=graph, **kw)
             torch.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
+            if rep == 2 and name == "greedy" and not graph:
+                torch.cuda.profiler.stop()
         t = min(ts)
         weights_mb = 193.2
         kv_gb = sum(36864 * (15 + j) for j in range(LENGTH)) * B / 1e9
