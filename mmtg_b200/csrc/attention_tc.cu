@@ -154,10 +154,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
       mbar_wait<15>(bar_s, (uint32_t)(j & 1));
       ATT_TRACE(21 + 100 * j);
       tc_fence_after();
+      // On the diagonal block every key of chunk c > warp lies in the causal future of all 32
+      // rows of this warp: those chunks are skipped (P = 0 written without reading S).
+      const int cmax = (j == qt) ? warp : TK / 32 - 1;
       // pass 1: row maximum
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < TK / 32; ++c) {
+      for (int c = 0; c <= cmax; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_addr + c * 32, v);
         tmem_ld_wait();
@@ -197,6 +200,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
       float rs = 0.f;
 #pragma unroll 1
       for (int c = 0; c < TK / 32; ++c) {
+        if (c > cmax) {  // warp-uniform
+          uint8_t* half = prow + (c >> 1) * 16384;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            *reinterpret_cast<uint4*>(half + ((((c & 1) * 4 + t) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          continue;
+        }
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_addr + c * 32, v);
         tmem_ld_wait();
@@ -449,8 +459,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     __syncwarp();
   } else {
-    // two threads per query row: warps 0-3 take key columns 0..63, warps 4-7 columns 64..127
-    // (a warp may only touch TMEM lanes 32*(warp%4) .. +31, any columns)
+    // two threads per query row: warps 0-3 take the even 32-key chunks, warps 4-7 the odd ones
+    // (a warp may only touch TMEM lanes 32*(warp%4) .. +31, any columns). On a diagonal pair
+    // every key of chunk c > warp%4 is in the causal future of all 32 rows of the warp: those
+    // chunks get P = dS = 0 without reading S / dP.
     const int r = (warp & 3) * 32 + lane;
     const int ch = warp >> 2;  // column half
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
@@ -483,7 +495,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
+        for (int c = ch; c < 4; c += 2) {
+          if (i == j && c > (warp & 3)) {  // warp-uniform
+            const int hoff = (c >> 1) * 16384;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int off = hoff + ((((c & 1) * 4 + t) ^ (r & 7)) << 4);
+              *reinterpret_cast<uint4*>(prow + off) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            continue;
+          }
           uint32_t sv[32], dv[32];
           tmem_ld_32x32(tS + lane_addr + c * 32, sv);
           tmem_ld_32x32(tDP + lane_addr + c * 32, dv);

@@ -731,7 +731,16 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr_set = true;
   }
   const int total = p.num_mp * p.num_n * p.splits;  // work units of a CTA pair
-  const int max_clusters = num_sms() / 2;
+  // MMTG_GEMM_CTAS caps the persistent grid (data-parallel runs leave a few SMs to the NCCL
+  // kernels: a persistent CTA pair that cannot become resident until an all-reduce kernel exits
+  // delays its statically assigned tiles, and with them the whole GEMM)
+  static const int cta_cap = []() {
+    const char* e = getenv("MMTG_GEMM_CTAS");
+    const int v = e ? atoi(e) : 0;
+    return v >= 2 ? v : 0;
+  }();
+  int max_clusters = num_sms() / 2;
+  if (cta_cap && cta_cap / 2 < max_clusters) max_clusters = cta_cap / 2;
   const int grid = 2 * (total < max_clusters ? total : max_clusters);
   ProfScope prof(0, 2.0 * p.M * p.N * p.K,
                  2.0 * ((double)p.M * p.K + (double)p.N * p.K) + (p.out_bf16 ? 2.0 : 4.0) * p.M * p.N, st);
