@@ -103,6 +103,10 @@ typedef struct mmtg_gemm_args {
   const uint64_t* drop_seed;
   uint32_t drop_site;
   float drop_p;
+  /* 0: persistent grid (one CTA per SM walks the tiles); 1: one work unit per CTA pair — short-lived
+   * CTAs for background work on a low-priority stream (weight gradients next to the backward chain) */
+  int32_t grid_mode;
+  int32_t _pad2;
 } mmtg_gemm_args;
 
 int mmtg_gemm_bf16(const mmtg_gemm_args* args, void* stream);

@@ -40,6 +40,7 @@ class GemmArgs(C.Structure):
         ("lse_partial", C.c_void_p),
         ("dact_tanh_out", C.c_int32), ("out2_mode", C.c_int32),
         ("drop_seed", C.c_void_p), ("drop_site", C.c_uint32), ("drop_p", C.c_float),
+        ("grid_mode", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 

@@ -50,7 +50,7 @@ struct Ws {
   // decoder backward
   bf16* dlogits16;
   float* dh;
-  bf16 *g16, *du, *dx, *datt, *dqkv, *dp1, *dE;
+  bf16 *g16x[2], *g16b, *du, *dx, *datt, *dqkv, *dp1, *dE;  // g16x: ping-pong by backward stage parity
   float* delta;
   // encoder forward
   bf16 *x_topic16, *x_mod16[2];
@@ -125,7 +125,9 @@ void carve(const mmtg_dims& d, uint8_t* base, Ws* w) {
   w->hf_sum = f32(d.B);
   w->dlogits16 = b16(M * d.Vp);
   w->dh = f32(M * E);
-  w->g16 = b16(M * E);
+  w->g16x[0] = b16(M * E);
+  w->g16x[1] = b16(M * E);
+  w->g16b = b16(M * E);
   w->du = b16(M * 4 * E);
   w->dx = b16(M * E);
   w->datt = b16(M * E);
@@ -229,7 +231,7 @@ inline DropSpec drop_spec(const mmtg_model* m, uint32_t site, float p, int mask_
 // split: pick the tile width and split count whose (tile pair x split) work units fill whole
 // waves of the 74 CTA-pair clusters, preferring fewer splits (fewer fp32 atomics) on ties.
 int wgrad(const bf16* X, long long ldx, const bf16* Y, long long ldy, float* dW, long long ldw,
-          int rows, int cols, int K, cudaStream_t st) {
+          int rows, int cols, int K, cudaStream_t st, int grid_mode = 0) {
   const int clusters = num_sms() / 2;
   const int pairs = (cdiv(rows, 128) + 1) / 2;
   const int nkb = cdiv(K, 64);
@@ -254,6 +256,7 @@ int wgrad(const bf16* X, long long ldx, const bf16* Y, long long ldy, float* dW,
   Gemm g(X, ldx, true, Y, ldy, true, rows, cols, K);
   g.out_f32(dW, ldw).accumulate(best_split);
   g.a.block_n = best_bn;
+  g.a.grid_mode = grid_mode;
   return g.run(st);
 }
 
@@ -402,6 +405,41 @@ extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void
   return 0;
 }
 
+namespace mmtg {
+namespace {
+// Weight-gradient GEMMs are off the backward's critical chain (only the optimizer consumes them):
+// they run on a side stream, forked after their operands exist and joined at the end of the
+// stage, so their CTAs fill the idle SMs of the chain's partial waves (the N = 768 dgrads run
+// 90 tile pairs on 74 clusters; the whole-head attention backward 384 CTAs on 148 SMs) instead
+// of queueing behind them. MMTG_WGRAD_STREAM=0 keeps everything on one stream.
+struct SideStream {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool used = false;
+};
+SideStream* side_stream() {
+  static const bool enabled = [] {
+    const char* e = getenv("MMTG_WGRAD_STREAM");
+    return !(e && e[0] == '0');
+  }();
+  if (!enabled) return nullptr;
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (!s.side) {
+    int lo = 0, hi = 0;  // lowest priority: the chain's kernels win SMs as they free up
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
+  }
+  return &s;
+}
+}  // namespace
+}  // namespace mmtg
+
 extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
                                    int64_t workspace_bytes, const float* g_kl, int32_t stage_begin,
                                    int32_t stage_end, void* stream) {
@@ -418,39 +456,63 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
   float* G = m->grads;
   const mmtg_param_offsets& o = m->off;
   const int B = d.B, S = d.S, He = d.He, Dw = d.Dw, E = d.E, SB = d.S * d.B, M = d.B * d.L;
+  SideStream* ss = side_stream();
+  static const int side_grid_mode = [] {
+    const char* e = getenv("MMTG_WGRAD_GRID");
+    return e ? atoi(e) : 0;
+  }();
+  const int wg = ss ? side_grid_mode : 0;
+  // run `fn(stream)` on the side stream, ordered after everything issued on `st` so far
+  auto on_side = [&](auto&& fn) -> int {
+    if (!ss) return fn(st);
+    MMTG_CUDA_OK(cudaEventRecord(ss->fork, st));
+    MMTG_CUDA_OK(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+    ss->used = true;
+    return fn(ss->side);
+  };
+  auto join_side = [&]() -> int {
+    if (ss && ss->used) {
+      MMTG_CUDA_OK(cudaEventRecord(ss->join, ss->side));
+      MMTG_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+      ss->used = false;
+    }
+    return 0;
+  };
 
   for (int stage = stage_begin; stage < stage_end; ++stage) {
+    bf16* g_in = w.g16x[stage & 1];         // bf16 gradient of this stage's input (from the stage before)
+    bf16* g_out = w.g16x[(stage + 1) & 1];  // ... emitted for the next stage
     if (stage == 0) {
       // ---------------- lm_head (tied wte) + ln_f ----------------
       // dxf = dlogits · wte  (B operand: wte [V,E] as MN-major [N=E, K=V])
       MMTG_TRY(Gemm(w.dlogits16, d.Vp, false, W + o.wte, E, true, M, E, d.V).out_bf16(w.dx, E).run(st));
       // dwte += dlogits^T · xf
-      MMTG_TRY(wgrad(w.dlogits16, d.Vp, w.xf, E, G + o.wte, E, d.V, E, M, st));
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(w.dlogits16, d.Vp, w.xf, E, G + o.wte, E, d.V, E, M, s2, wg); }));
       // also emits g16 = bf16(dh) and the mlp c_proj bias gradient of the top block
       // (masked by the top block's mlp resid dropout: g16 is the gradient of the c_proj OUTPUT)
       const DropSpec dr = drop_spec(m, 4u * (d.NL - 1) + 2, m->p_resid);
       MMTG_TRY(layernorm_bwd(w.dx, 1, w.layer[d.NL - 1].h_out, w.meanf, w.rstdf, P + o.lnf_w, w.dh, 0,
-                             G + o.lnf_w, G + o.lnf_b, w.g16, G + o.layer[d.NL - 1].proj2_b, M, E, st, &dr));
+                             G + o.lnf_w, G + o.lnf_b, g_out, G + o.layer[d.NL - 1].proj2_b, M, E, st, &dr));
     } else if (stage <= d.NL) {
       const int l = d.NL - stage;
       const LayerWs& L = w.layer[l];
       const mmtg_layer_offsets& lo = o.layer[l];
       // ---- MLP ---- (g16 = bf16(dh) and d(proj2_b) were produced by the LayerNorm backward above)
-      MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj2_w, E, false, M, 4 * E, E)
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.a, 4 * E, g_in, E, G + lo.proj2_w, E, 4 * E, E, M, s2, wg); }));
+      MMTG_TRY(Gemm(g_in, E, false, W + lo.proj2_w, E, false, M, 4 * E, E)
                    .out_bf16(w.du, 4 * E).dmul(L.u, 4 * E).colsum(G + lo.fc_b).run(st));
-      MMTG_TRY(wgrad(L.a, 4 * E, w.g16, E, G + lo.proj2_w, E, 4 * E, E, M, st));
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, s2, wg); }));
       MMTG_TRY(Gemm(w.du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(w.dx, E).run(st));
-      MMTG_TRY(wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, st));
       const DropSpec d_att = drop_spec(m, 4u * l, m->p_attn), d_r1 = drop_spec(m, 4u * l + 1, m->p_resid);
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_mid, L.mean2, L.rstd2, P + lo.ln2_w, w.dh, 1, G + lo.ln2_w,
-                             G + lo.ln2_b, w.g16, G + lo.proj_b, M, E, st, &d_r1));
+                             G + lo.ln2_b, w.g16b, G + lo.proj_b, M, E, st, &d_r1));
       // ---- attention ----
-      MMTG_TRY(Gemm(w.g16, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(w.datt, E).run(st));
-      MMTG_TRY(wgrad(L.att, E, w.g16, E, G + lo.proj_w, E, E, E, M, st));
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.att, E, w.g16b, E, G + lo.proj_w, E, E, E, M, s2, wg); }));
+      MMTG_TRY(Gemm(w.g16b, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(w.datt, E).run(st));
       MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, w.datt, L.lse, w.delta, w.dqkv, B, d.L, d.NH, st, &d_att));
       MMTG_TRY(colsum(w.dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, st));
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, s2, wg); }));
       MMTG_TRY(Gemm(w.dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(w.dx, E).run(st));
-      MMTG_TRY(wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, st));
       // dh is now the gradient of this block's input: its bf16 copy / column sums feed the block
       // below (mlp c_proj bias) or, for block 0, the projector (projector_layer2 bias)
       // (masked by the dropout that produced this block's input: the mlp resid dropout of the
@@ -458,18 +520,18 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       const DropSpec d_in = l > 0 ? drop_spec(m, 4u * (l - 1) + 2, m->p_resid)
                                   : drop_spec(m, MMTG_DROP_SITE_EMBD, m->p_embd, 1);
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_in, L.mean1, L.rstd1, P + lo.ln1_w, w.dh, 1, G + lo.ln1_w,
-                             G + lo.ln1_b, w.g16, l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, st,
+                             G + lo.ln1_b, g_out, l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, st,
                              &d_in));
     } else {
       // ---------------- embeddings + projector ----------------
       MMTG_TRY(posadd_bwd(w.dh, G + o.wpe, B, d.L, E, st));
       MMTG_TRY(typeadd_bwd(w.dh, b->type_ids, G + o.wte, M, E, st));
       // dp1 = (g · W2) ⊙ (1 - p1²); W2 [E,He] as MN-major [N=He, K=E]
-      MMTG_TRY(Gemm(w.g16, E, false, W + o.proj2_w, He, true, M, He, E)
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(g_in, E, w.p1, He, G + o.proj2_w, He, E, He, M, s2, wg); }));
+      MMTG_TRY(Gemm(g_in, E, false, W + o.proj2_w, He, true, M, He, E)
                    .out_bf16(w.dp1, He).dtanh(w.p1, He).colsum(G + o.proj1_b).run(st));
-      MMTG_TRY(wgrad(w.g16, E, w.p1, He, G + o.proj2_w, He, E, He, M, st));
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(w.dp1, He, w.emb16, Dw, G + o.proj1_w, Dw, He, Dw, M, s2, wg); }));
       MMTG_TRY(Gemm(w.dp1, He, false, W + o.proj1_w, Dw, true, M, Dw, He).out_bf16(w.dE, Dw).run(st));
-      MMTG_TRY(wgrad(w.dp1, He, w.emb16, Dw, G + o.proj1_w, Dw, He, Dw, M, st));
       MMTG_TRY(embed_bwd(w.dE, w.dctx16, nullptr, B, d.P, d.T, S, d.two_sent, Dw, st));
       // ---------------- beta gate ----------------
       MMTG_TRY(colsum(w.dctx16, 1, Dw, nullptr, 0, G + o.beta_out_b, SB, Dw, st));
@@ -513,6 +575,9 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
                          3 * He, He, (S - 1) * B, st));
       }
     }
+    // side-stream weight gradients of this stage are complete before the next stage reuses
+    // du / dqkv / g16 (and before the caller all-reduces this stage's gradient bucket)
+    MMTG_TRY(join_side());
   }
   return 0;
 }

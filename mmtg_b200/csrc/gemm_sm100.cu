@@ -60,6 +60,7 @@ struct GemmParams {
   const unsigned long long* drop_seed;
   uint32_t drop_site;
   float drop_p;
+  int grid_mode;
 };
 
 // TWO = cta_group::2: the pair's 256 x BN tile is ONE MMA; each CTA stages its own 128 A rows and
@@ -741,6 +742,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }();
   int max_clusters = num_sms() / 2;
   if (cta_cap && cta_cap / 2 < max_clusters) max_clusters = cta_cap / 2;
+  if (p.grid_mode == 1) max_clusters = total;  // one work unit per CTA pair
   const int grid = 2 * (total < max_clusters ? total : max_clusters);
   ProfScope prof(0, 2.0 * p.M * p.N * p.K,
                  2.0 * ((double)p.M * p.K + (double)p.N * p.K) + (p.out_bf16 ? 2.0 : 4.0) * p.M * p.N, st);
@@ -814,6 +816,7 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
   p.dact_tanh_out = a->dact_tanh_out;
   p.drop_seed = (const unsigned long long*)a->drop_seed; p.drop_site = a->drop_site;
   p.drop_p = a->drop_seed ? a->drop_p : 0.f;
+  p.grid_mode = a->grid_mode;
   p.out2_mode = a->out2_mode;
   MMTG_CHECK_ARG(!(p.lse_partial && p.splits > 1), "lse_partial is incompatible with split_k");
   {

@@ -24,7 +24,11 @@ class GraphedTrainStep:
         self.alpha, self.stage = alpha, stage
         self.static = {k: v.detach().clone() for k, v in example_batch.items()}
         self.sync = model.grad_sync
-        side = torch.cuda.Stream()
+        # capture on a HIGH-priority stream: the engine's weight-gradient side stream has the lowest
+        # priority, so the backward chain's kernels win SMs as they free up (priorities are kept
+        # in the captured kernel nodes)
+        side = torch.cuda.Stream(priority=-1)
+        self.cap_stream = side
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -33,23 +37,23 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         if self.sync is None:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=self.cap_stream):
                 self.total = self._eager()
             return
         # segmented capture: collectives are issued eagerly between the segments
         self.g_fwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fwd):
+        with torch.cuda.graph(self.g_fwd, stream=self.cap_stream):
             self.step, self.total, _, _ = model.fused_forward_loss(self.static, stage, alpha)
         pool = self.g_fwd.pool()
         self.nstage = self.step.dims.NL + 2
         self.g_stage = []
         for s in range(self.nstage):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
                 model.backward_stages(self.step, s, s + 1)
             self.g_stage.append(g)
         self.g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_opt, pool=pool):
+        with torch.cuda.graph(self.g_opt, pool=pool, stream=self.cap_stream):
             optimizer.step()
             optimizer.zero_grad()
 
