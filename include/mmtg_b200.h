@@ -250,10 +250,11 @@ int mmtg_dlogits_from_f32(const mmtg_dims* dims, void* workspace, const float* d
  * the embedding sum [B*L,E]. mmtg_dropout_mask materialises keep flags (1 = kept) of elements
  * [0, n) of a site for tests; mmtg_dropout_next_seed advances the device-side seed (capturable). */
 int mmtg_attn_fwd_drop(const void* qkv, const int32_t* key_mask, void* out, float* lse, int32_t B, int32_t L,
-                       int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p, void* stream);
+                       int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p, int32_t impl,
+                       void* stream);
 int mmtg_attn_bwd_drop(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,
                        const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L, int32_t n_head,
-                       const uint64_t* seed_dev, uint32_t site, float p, void* stream);
+                       const uint64_t* seed_dev, uint32_t site, float p, int32_t impl, void* stream);
 #define MMTG_DROP_SITE_EMBD 0xFFFFu
 int mmtg_dropout_mask(const uint64_t* seed_dev, uint32_t site, float p, int64_t n, uint8_t* keep_out, void* stream);
 int mmtg_dropout_next_seed(uint64_t* seed_dev, void* stream);

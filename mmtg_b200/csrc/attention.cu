@@ -34,7 +34,16 @@ struct AttnParams {
   bf16* dqkv;       // [B*L, 3E]
   int B, L, NH, E;
   float scale;
+  // dropout of the probabilities: element ((b*NH+h)*L + q) * Lp + key, Lp = L rounded up to even
+  const unsigned long long* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
 };
+
+// pair index (two neighbouring keys share one hash) of element (q, key) of head bh
+__device__ __forceinline__ uint32_t attn_pair(int bh, int L, int q, int key) {
+  return (uint32_t)(bh * L + q) * (uint32_t)((L + 1) >> 1) + (uint32_t)(key >> 1);
+}
 
 // --------------------------------------------------------------------------------------------
 // forward
@@ -48,6 +57,9 @@ attn_fwd_kernel(const AttnParams p) {
 
   const int qb = (gridDim.x - 1) - blockIdx.x;  // heavy (late) query blocks first
   const int bh = blockIdx.y;
+  const bool dropping = p.drop_p > 0.f;
+  DropKey dkey = {0u, 0u, 0u, 1.f};
+  if (dropping) dkey = drop_key(p.drop_seed, p.drop_site, p.drop_p);
   const int b = bh / p.NH, h = bh - b * p.NH;
   const int warp = threadIdx.x >> 5, l = lane_id();
   const long long ld = 3LL * p.E;
@@ -128,6 +140,15 @@ attn_fwd_kernel(const AttnParams p) {
         s[nb][j] = e;
         rs[j >> 1] += e;
       }
+      if (dropping) {  // O uses the dropped P; the 1/(1-p) factor is applied at the end
+        const int key = t * BKV + nb * 8 + (l & 3) * 2;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t bits = drop_bits(dkey, attn_pair(bh, p.L, row_lo + r * 8, key));
+          if (!drop_keep_lo(dkey, bits)) s[nb][2 * r] = 0.f;
+          if (!drop_keep_hi(dkey, bits)) s[nb][2 * r + 1] = 0.f;
+        }
+      }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
@@ -150,7 +171,7 @@ attn_fwd_kernel(const AttnParams p) {
   for (int r = 0; r < 2; ++r) {
     const int row = row_lo + r * 8;
     if (row < p.L) {
-      const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+      const float inv = (l_run[r] > 0.f ? 1.f / l_run[r] : 0.f) * dkey.inv_keep;
       bf16* dst = p.out + ((long long)b * p.L + row) * p.E + h * HD + (l & 3) * 2;
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb)
@@ -208,6 +229,9 @@ attn_bwd_dkdv_kernel(const AttnParams p) {
 
   const int kb = blockIdx.x;
   const int bh = blockIdx.y;
+  const bool dropping = p.drop_p > 0.f;
+  DropKey dkey = {0u, 0u, 0u, 1.f};
+  if (dropping) dkey = drop_key(p.drop_seed, p.drop_site, p.drop_p);
   const int b = bh / p.NH, h = bh - b * p.NH;
   const int warp = threadIdx.x >> 5, l = lane_id();
   const long long ld = 3LL * p.E;
@@ -275,7 +299,29 @@ attn_bwd_dkdv_kernel(const AttnParams p) {
         st[nb][j] = ok ? exp2f(st[nb][j] * sl2 - sLse[buf][qc]) : 0.f;  // P^T
       }
     }
-    mma_nn(dv, st, sdO[buf]);  // dV += P^T dO
+    // with dropout D = keep/(1-p): dV += (P.D)^T dO and dS = P (D.dP - delta)
+    float dm[8][4];
+    if (dropping) {
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = t * BQ + nb * 8 + (l & 3) * 2 + (j & 1);
+          const int key = key_lo + (j >> 1) * 8;
+          const uint32_t bits = drop_bits(dkey, attn_pair(bh, p.L, q, key));
+          const bool keep = (key & 1) ? drop_keep_hi(dkey, bits) : drop_keep_lo(dkey, bits);
+          dm[nb][j] = keep ? dkey.inv_keep : 0.f;
+        }
+      }
+      float pd[8][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pd[nb][j] = st[nb][j] * dm[nb][j];
+      mma_nn(dv, pd, sdO[buf]);
+    } else {
+      mma_nn(dv, st, sdO[buf]);  // dV += P^T dO
+    }
     // dP^T = V dO^T
     float dpt[8][4];
 #pragma unroll
@@ -288,7 +334,8 @@ attn_bwd_dkdv_kernel(const AttnParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int qc = nb * 8 + (l & 3) * 2 + (j & 1);
-        dpt[nb][j] = st[nb][j] * (dpt[nb][j] - sDelta[buf][qc]);  // dS^T
+        const float dpd = dropping ? dpt[nb][j] * dm[nb][j] : dpt[nb][j];
+        dpt[nb][j] = st[nb][j] * (dpd - sDelta[buf][qc]);  // dS^T
       }
     }
     mma_nn(dk, dpt, sQ[buf]);  // dK += dS^T Q
@@ -325,6 +372,9 @@ attn_bwd_dq_kernel(const AttnParams p) {
 
   const int qb = (gridDim.x - 1) - blockIdx.x;
   const int bh = blockIdx.y;
+  const bool dropping = p.drop_p > 0.f;
+  DropKey dkey = {0u, 0u, 0u, 1.f};
+  if (dropping) dkey = drop_key(p.drop_seed, p.drop_site, p.drop_p);
   const int b = bh / p.NH, h = bh - b * p.NH;
   const int warp = threadIdx.x >> 5, l = lane_id();
   const long long ld = 3LL * p.E;
@@ -391,7 +441,12 @@ attn_bwd_dq_kernel(const AttnParams p) {
         const int row = row_lo + (j >> 1) * 8;
         const float pv = (key <= row && sMask[buf][kc] == 0.f)
                              ? exp2f(s[nb][j] * sl2 - lse2[j >> 1]) : 0.f;
-        s[nb][j] = pv * (dp[nb][j] - dl[j >> 1]);  // dS
+        float dpd = dp[nb][j];
+        if (dropping) {
+          const uint32_t bits = drop_bits(dkey, attn_pair(bh, p.L, row, key));
+          dpd = ((key & 1) ? drop_keep_hi(dkey, bits) : drop_keep_lo(dkey, bits)) ? dpd * dkey.inv_keep : 0.f;
+        }
+        s[nb][j] = pv * (dpd - dl[j >> 1]);  // dS
       }
     }
     mma_nn(dq, s, sK[buf]);  // dQ += dS K
@@ -427,10 +482,10 @@ int attn_fwd_impl(const bf16* qkv, const int* kmask, bf16* out, float* lse, int 
   }();
   const bool use_tc = impl == 2 || (impl == 0 && env_tc);
   if (use_tc) return attn_fwd_tc(qkv, kmask, out, lse, B, L, NH, st, drop);
-  MMTG_CHECK_ARG(!drop_on(drop), "attention dropout is implemented by the tcgen05 kernels only (MMTG_ATTN_TC=0 / impl 1 not supported)");
   AttnParams p{};
   p.qkv = qkv; p.kmask = kmask; p.out = out; p.lse = lse;
   p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
+  if (drop_on(drop)) { p.drop_seed = drop->seed; p.drop_site = drop->site; p.drop_p = drop->p; }
   dim3 grid(cdiv(L, BQ), B * NH);
   // causal FLOPs: 2 GEMMs x 2 x 64 x L(L+1)/2 per (b, h)
   ProfScope prof(1, 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 4 * B * L * NH * 64, st);
@@ -461,6 +516,7 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
   AttnParams p{};
   p.qkv = qkv; p.kmask = kmask; p.lse = const_cast<float*>(lse); p.dout = dout; p.delta = delta;
   p.dqkv = dqkv; p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
+  if (drop_on(drop)) { p.drop_seed = drop->seed; p.drop_site = drop->site; p.drop_p = drop->p; }
   ProfScope prof(1, 2.5 * 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 8 * B * L * NH * 64, st);
   const long long warps = (long long)B * L;
   attn_delta_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, st>>>(out, dout, delta, B, L, NH, p.E);
@@ -469,7 +525,6 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
     count_launch();
     return attn_bwd_tc(qkv, kmask, dout, lse, delta, dqkv, B, L, NH, st, drop);
   }
-  MMTG_CHECK_ARG(!drop_on(drop), "attention dropout backward needs the tcgen05 kernel (L <= 256, MMTG_ATTN_BWD_TC != 0)");
   dim3 grid(cdiv(L, BQ), B * NH);
   constexpr int BWD_SMEM = 6 * BQ * HD * 2 + 4 * BQ * 4;  // 6 bf16 tiles + 4 x 64 floats
   static bool attr_set = false;
@@ -513,19 +568,22 @@ extern "C" int mmtg_attn_bwd_ex(const void* qkv, const int32_t* key_mask, const 
 // dropout variants (tcgen05 kernels): probabilities masked by (seed, site) with keep-rate 1 - p
 extern "C" int mmtg_attn_fwd_drop(const void* qkv, const int32_t* key_mask, void* out, float* lse, int32_t B,
                                   int32_t L, int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p,
-                                  void* stream) {
-  MMTG_CHECK_ARG(qkv && out && B > 0 && L > 0 && n_head > 0 && p >= 0.f && p < 1.f, "bad attention args");
+                                  int32_t impl, void* stream) {
+  MMTG_CHECK_ARG(qkv && out && B > 0 && L > 0 && n_head > 0 && p >= 0.f && p < 1.f && impl >= 0 && impl <= 2,
+                 "bad attention args");
   DropSpec d{(const unsigned long long*)seed_dev, site, p, 0};
-  return attn_fwd_impl((const bf16*)qkv, key_mask, (bf16*)out, lse, B, L, n_head, 2, (cudaStream_t)stream, &d);
+  return attn_fwd_impl((const bf16*)qkv, key_mask, (bf16*)out, lse, B, L, n_head, impl, (cudaStream_t)stream, &d);
 }
 extern "C" int mmtg_attn_bwd_drop(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,
                                   const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L,
-                                  int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p, void* stream) {
-  MMTG_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && L > 0 && L <= 256 && n_head > 0 &&
-                     p >= 0.f && p < 1.f, "bad attention bwd args (dropout backward handles L <= 256)");
+                                  int32_t n_head, const uint64_t* seed_dev, uint32_t site, float p, int32_t impl,
+                                  void* stream) {
+  MMTG_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && L > 0 && n_head > 0 && p >= 0.f &&
+                     p < 1.f && impl >= 0 && impl <= 2, "bad attention bwd args");
+  MMTG_CHECK_ARG(!(impl == 2 && L > 256), "tcgen05 attention backward handles L <= 256");
   DropSpec d{(const unsigned long long*)seed_dev, site, p, 0};
   return attn_bwd_impl((const bf16*)qkv, key_mask, (const bf16*)out, (const bf16*)dout, lse, delta_ws,
-                       (bf16*)dqkv, B, L, n_head, 2, (cudaStream_t)stream, &d);
+                       (bf16*)dqkv, B, L, n_head, impl, (cudaStream_t)stream, &d);
 }
 
 extern "C" int mmtg_attn_fwd(const void* qkv, const int32_t* key_mask, void* out, float* lse,

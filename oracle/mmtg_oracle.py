@@ -242,7 +242,8 @@ def mmtg_forward(sd, table, batch, data_config, train_flag=True, dropout=None):
         labels = torch.zeros(emb.shape[0], emb.shape[1], dtype=torch.long)
     h1 = torch.tanh(emb @ sd["decoder.projector_layer1.weight"].t() + sd["decoder.projector_layer1.bias"])
     x = h1 @ sd["decoder.projector_layer2.weight"].t() + sd["decoder.projector_layer2.bias"]
-    logits = gpt2_forward(sd, x, types, mask, dropout=dropout)
+    n_layer = sum(1 for k in sd if k.startswith("decoder.gpt2.transformer.h.") and k.endswith(".ln_1.weight"))
+    logits = gpt2_forward(sd, x, types, mask, n_layer=n_layer, dropout=dropout)
     return hf_causal_lm_loss(logits, labels), kl, logits
 
 

@@ -44,8 +44,9 @@ def test_mask_statistics_and_streams(cuda):
     assert abs(_mask(seed, 9, 0.5, n, cuda).float().mean().item() - 0.5) < 2e-3
 
 
-@pytest.mark.parametrize("L", [236, 100, 128])
-def test_attention_dropout_matches_masked_reference(cuda, L):
+@pytest.mark.parametrize("L,impl", [(236, 2), (100, 2), (128, 2), (236, 1), (300, 1), (77, 1), (300, 0)])
+def test_attention_dropout_matches_masked_reference(cuda, L, impl):
+    """impl 2 = tcgen05 kernels, 1 = mma.sync kernels (the backward for L > 256), 0 = default dispatch."""
     from mmtg_b200 import _lib
     lib = _lib.lib()
     B, NH, E, p, site = 2, 12, 768, 0.1, 4 * 3
@@ -63,10 +64,10 @@ def test_attention_dropout_matches_masked_reference(cuda, L):
     st = C.c_void_p(_lib.stream_ptr())
     vp = C.c_void_p
     _lib.check(lib.mmtg_attn_fwd_drop(vp(qkv.data_ptr()), vp(kmask.data_ptr()), vp(out.data_ptr()), vp(lse.data_ptr()),
-                                      B, L, NH, vp(seed.data_ptr()), C.c_uint32(site), C.c_float(p), st), "attn_fwd_drop")
+                                      B, L, NH, vp(seed.data_ptr()), C.c_uint32(site), C.c_float(p), impl, st), "attn_fwd_drop")
     _lib.check(lib.mmtg_attn_bwd_drop(vp(qkv.data_ptr()), vp(kmask.data_ptr()), vp(out.data_ptr()), vp(dout.data_ptr()),
                                       vp(lse.data_ptr()), vp(delta.data_ptr()), vp(dqkv.data_ptr()), B, L, NH,
-                                      vp(seed.data_ptr()), C.c_uint32(site), C.c_float(p), st), "attn_bwd_drop")
+                                      vp(seed.data_ptr()), C.c_uint32(site), C.c_float(p), impl, st), "attn_bwd_drop")
     Lp = (L + 1) // 2 * 2
     keep = _mask(seed, site, p, B * NH * L * Lp, cuda).view(B, NH, L, Lp)[..., :L].float()
     x = qkv.float().view(B, L, 3, NH, 64).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
@@ -83,7 +84,7 @@ def test_attention_dropout_matches_masked_reference(cuda, L):
     # and the masks actually bite: p = 0 gives a different output
     out0 = torch.empty_like(out)
     _lib.check(lib.mmtg_attn_fwd_drop(vp(qkv.data_ptr()), vp(kmask.data_ptr()), vp(out0.data_ptr()), vp(lse.data_ptr()),
-                                      B, L, NH, vp(seed.data_ptr()), C.c_uint32(site), C.c_float(0.0), st), "attn_fwd_drop")
+                                      B, L, NH, vp(seed.data_ptr()), C.c_uint32(site), C.c_float(0.0), impl, st), "attn_fwd_drop")
     assert (out0.float() - out.float()).abs().max().item() > 0.05
 
 
@@ -101,20 +102,26 @@ def _site_masks(model, d, cuda):
     return m
 
 
-def test_train_step_with_dropout_matches_masked_oracle(cuda):
+@pytest.mark.parametrize("n_layer,max_sent_length", [(12, None), (2, 30)])
+def test_train_step_with_dropout_matches_masked_oracle(cuda, n_layer, max_sent_length):
+    """(12, default): the benchmark configuration (L = 236, tcgen05 attention both ways);
+    (2, 30): extended lyrics length (L = 336): the backward runs the mma.sync attention kernels."""
     from mmtg_b200 import synth
-    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200.configs import data_config as _dc, model_cfgs
     from mmtg_b200.loss import MyLoss
     from mmtg_b200.model import MMTG
     from oracle import mmtg_oracle as O
     table = synth.make_token_table()
-    sd = synth.make_state_dict(0)
-    model = MMTG(model_cfgs, data_config(), 13317, train_flag=True, token_table=table)
+    g2 = {"n_layer": n_layer}
+    dcfg = _dc() if max_sent_length is None else _dc(max_sent_length=max_sent_length)
+    data_config = lambda: dcfg
+    sd = synth.make_state_dict(0, gpt2_cfg=g2)
+    model = MMTG(model_cfgs, dcfg, 13317, train_flag=True, token_table=table, gpt2_config=g2)
     model.load_state_dict(sd)
     model.to(cuda)
     assert model._drop_p == (0.1, 0.1, 0.1) and model.dropout_active()
     model.set_dropout_seed(4242)
-    host = synth.batch_to_torch(synth.make_batch(2, seed=31, ratings=np.array([4, 1])))
+    host = synth.batch_to_torch(synth.make_batch(2, seed=31, data_config=dcfg, ratings=np.array([4, 1])))
     dev = {k: v.to(cuda) for k, v in host.items()}
     crit = MyLoss(data_config(), model_cfgs)
     model.zero_grad(set_to_none=True)
