@@ -282,6 +282,7 @@ def main():
     import ctypes as C
     lib.mmtg_prof_reset()
     lib.mmtg_prof_enable(1)
+    lib.mmtg_set_wgrad_side_stream(0)  # per-launch event times must not include a concurrent kernel
     PROF_STEPS = 2
     lp0 = lib.mmtg_launch_count()
     for _ in range(PROF_STEPS):  # profiled steps always launch eagerly (events per launch)
@@ -289,6 +290,7 @@ def main():
         eager_step(resident)
     torch.cuda.synchronize()
     lib.mmtg_prof_enable(0)
+    lib.mmtg_set_wgrad_side_stream(1)
     launches_per_step = int(lib.mmtg_launch_count() - lp0) // PROF_STEPS
     if use_graph:  # replays bypass the library's launch counter: same kernels, K replays
         launches = launches_per_step * K

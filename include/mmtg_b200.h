@@ -243,6 +243,8 @@ void* mmtg_ws_dlogits_bf16(const mmtg_dims* dims, void* workspace);  /* [B*L, Vp
 int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
                         int64_t workspace_bytes, const float* g_kl, int32_t stage_begin,
                         int32_t stage_end, void* stream);
+/* weight-gradient GEMMs on a low-priority side stream inside mmtg_train_backward (default 1) */
+int mmtg_set_wgrad_side_stream(int32_t enable);
 int mmtg_dlogits_from_f32(const mmtg_dims* dims, void* workspace, const float* dlogits_f32, void* stream);
 
 /* Dropout sites: block l uses 4*l + {0: attention probabilities [B,NH,L,L'] with L' = L rounded

@@ -417,12 +417,13 @@ struct SideStream {
   cudaEvent_t fork = nullptr, join = nullptr;
   bool used = false;
 };
+int g_side_enabled = -1;  // -1: from MMTG_WGRAD_STREAM (default on); 0 / 1: mmtg_set_wgrad_side_stream
 SideStream* side_stream() {
-  static const bool enabled = [] {
+  if (g_side_enabled < 0) {
     const char* e = getenv("MMTG_WGRAD_STREAM");
-    return !(e && e[0] == '0');
-  }();
-  if (!enabled) return nullptr;
+    g_side_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_side_enabled) return nullptr;
   static SideStream per_dev[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
@@ -439,6 +440,14 @@ SideStream* side_stream() {
 }
 }  // namespace
 }  // namespace mmtg
+
+// Run the weight-gradient GEMMs of mmtg_train_backward on the low-priority side stream (1,
+// default) or inline on the caller's stream (0: per-launch timings are then not perturbed by
+// concurrent kernels — bench.py's profiled steps).
+extern "C" int mmtg_set_wgrad_side_stream(int32_t enable) {
+  mmtg::g_side_enabled = enable ? 1 : 0;
+  return 0;
+}
 
 extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, void* workspace,
                                    int64_t workspace_bytes, const float* g_kl, int32_t stage_begin,
@@ -499,9 +508,14 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       const mmtg_layer_offsets& lo = o.layer[l];
       // ---- MLP ---- (g16 = bf16(dh) and d(proj2_b) were produced by the LayerNorm backward above)
       MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.a, 4 * E, g_in, E, G + lo.proj2_w, E, 4 * E, E, M, s2, wg); }));
+      // (the c_fc bias gradient = column sums of du is a separate HBM-bound pass on the side
+      // stream: fused into this epilogue it cost 13 us of the critical chain, measured)
       MMTG_TRY(Gemm(g_in, E, false, W + lo.proj2_w, E, false, M, 4 * E, E)
-                   .out_bf16(w.du, 4 * E).dmul(L.u, 4 * E).colsum(G + lo.fc_b).run(st));
-      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, s2, wg); }));
+                   .out_bf16(w.du, 4 * E).dmul(L.u, 4 * E).run(st));
+      MMTG_TRY(on_side([&](cudaStream_t s2) {
+        MMTG_TRY(colsum(w.du, 1, 4 * E, nullptr, 0, G + lo.fc_b, M, 4 * E, s2));
+        return wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, s2, wg);
+      }));
       MMTG_TRY(Gemm(w.du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(w.dx, E).run(st));
       const DropSpec d_att = drop_spec(m, 4u * l, m->p_attn), d_r1 = drop_spec(m, 4u * l + 1, m->p_resid);
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_mid, L.mean2, L.rstd2, P + lo.ln2_w, w.dh, 1, G + lo.ln2_w,
@@ -510,8 +524,10 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.att, E, w.g16b, E, G + lo.proj_w, E, E, E, M, s2, wg); }));
       MMTG_TRY(Gemm(w.g16b, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(w.datt, E).run(st));
       MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, w.datt, L.lse, w.delta, w.dqkv, B, d.L, d.NH, st, &d_att));
-      MMTG_TRY(colsum(w.dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, st));
-      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, s2, wg); }));
+      MMTG_TRY(on_side([&](cudaStream_t s2) {
+        MMTG_TRY(colsum(w.dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, s2));
+        return wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, s2, wg);
+      }));
       MMTG_TRY(Gemm(w.dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(w.dx, E).run(st));
       // dh is now the gradient of this block's input: its bf16 copy / column sums feed the block
       // below (mlp c_proj bias) or, for block 0, the projector (projector_layer2 bias)

@@ -27,15 +27,32 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib.mmtg_last_error(), bytes)
 
 
-def test_ctypes_structs_match_header_sizes():
+def test_ctypes_structs_match_header_sizes(tmp_path):
+    """The ctypes mirrors against the C compiler's view of include/mmtg_b200.h (sizes and the
+    offsets of the last fields), not against hand-counted constants."""
+    import subprocess
     from mmtg_b200 import _lib
     from mmtg_b200.model import Batch, Dims, LayerOffsets, Model, ParamOffsets
-    assert ctypes.sizeof(Dims) == 16 * 4
-    assert ctypes.sizeof(LayerOffsets) == 12 * 8
-    assert ctypes.sizeof(ParamOffsets) == (2 + 8 + 6 + 4 + 4 + 4 + 4) * 8 + 48 * 12 * 8
-    assert ctypes.sizeof(Batch) == 7 * 8
-    assert ctypes.sizeof(Model) == ctypes.sizeof(Dims) + ctypes.sizeof(ParamOffsets) + 4 * 8
-    assert ctypes.sizeof(_lib.GemmArgs) % 8 == 0
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "mmtg_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mmtg_dims), sizeof(mmtg_layer_offsets),\n'
+        "         sizeof(mmtg_param_offsets), sizeof(mmtg_batch), sizeof(mmtg_model), sizeof(mmtg_gemm_args),\n"
+        "         offsetof(mmtg_model, p_attn), offsetof(mmtg_gemm_args, drop_p), offsetof(mmtg_gemm_args, grid_mode));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "sz"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    c = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert ctypes.sizeof(Dims) == c[0] == 16 * 4
+    assert ctypes.sizeof(LayerOffsets) == c[1]
+    assert ctypes.sizeof(ParamOffsets) == c[2]
+    assert ctypes.sizeof(Batch) == c[3]
+    assert ctypes.sizeof(Model) == c[4]
+    assert ctypes.sizeof(_lib.GemmArgs) == c[5]
+    assert Model.p_attn.offset == c[6]
+    assert _lib.GemmArgs.drop_p.offset == c[7] and _lib.GemmArgs.grid_mode.offset == c[8]
 
 
 def test_workspace_size_query_runs_without_gpu():
