@@ -138,6 +138,37 @@ def cpu_train_step_time(batch_size, reps, threads):
     return float(np.median(ts))
 
 
+def gpu_eager_step_time(batch_size, reps, dev, autocast):
+    """The same restated reference step run by PyTorch eager (cuBLAS / SDPA-free plain ops) on the
+    B200 itself: "the Blackwell kernels to beat" (SURVEY §8d second reported baseline).
+    Oracle code, baseline leg only. Returns s/step (CUDA events)."""
+    from mmtg_b200 import synth
+    from mmtg_b200.configs import data_config
+    from oracle import mmtg_oracle as O
+    table = torch.from_numpy(synth.make_token_table()).to(dev)
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(0).items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "decoder.gpt2.lm_head.weight"}
+    params["decoder.gpt2.lm_head.weight"] = params["decoder.gpt2.transformer.wte.weight"]
+    batch = {k: v.to(dev) for k, v in synth.batch_to_torch(synth.make_batch(batch_size, seed=1234)).items()}
+    ts = []
+    for i in range(reps + 1):
+        for p in params.values():
+            p.grad = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            hf, kl, logits = O.mmtg_forward(params, table, batch, data_config(), True)
+        total = O.my_loss(logits.float(), batch["targets"], batch["rating"], STAGE).mean() + ALPHA * kl.float().mean()
+        total.backward()
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            ts.append(e0.elapsed_time(e1) / 1e3)
+    del params, sd, logits, total
+    torch.cuda.empty_cache()
+    return float(np.median(ts))
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -359,6 +390,15 @@ def main():
             sec = cpu_train_step_time(2, 3, threads)
             line["cpu_baseline"] = {"value": 2 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
                                     "sample": "3 timed steps of batch 2 (L=236) after 1 warm-up, oracle/mmtg_oracle.py fwd+MyLoss+KL+autograd bwd, fp32"}
+            try:  # second reported baseline: the oracle in PyTorch eager on this GPU (forward+backward only)
+                bs = 32
+                line["torch_eager_gpu_baseline"] = {
+                    "unit": "samples/s", "batch": bs,
+                    "fp32": bs / gpu_eager_step_time(bs, 3, dev, False),
+                    "bf16_autocast": bs / gpu_eager_step_time(bs, 3, dev, True),
+                    "sample": "oracle/mmtg_oracle.py fwd + MyLoss + KL + autograd bwd (no optimizer), 3 timed steps, CUDA events"}
+            except Exception as e:  # reported baseline only: never fails the bench
+                line["torch_eager_gpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -249,3 +249,38 @@ def postprocess_tokens(tokens):
     while text and text[-1] == "，":
         text = text[:-1]
     return text
+
+
+def generate_samples(model, dataset, tokenizer, n_samples=10, length=None, start_token="[#START#]", temperature=1.1,
+                     top_k=10, top_p=0.7, repitition_penalty=1.5, device="cuda", rows_per_call=64, seed=0,
+                     save_path=None, _sampler=None):
+    """The reference's generation front-end (src/generate.py:203-244) over the batched decoder:
+    for every dataset item, `n_samples` independent runs of `sample_sequence` started from
+    `[#START#]`, detokenised and post-processed with `postprocess_tokens`; one output line per
+    sample, items in dataset order (written to `save_path` when given). The (item, sample) runs
+    are independent batch-1 reference runs, so they are packed `rows_per_call` at a time into
+    `sample_sequence_batch` (the reference decodes them one after another).
+    `dataset[i]` is a MyDataset item (dict of arrays); `tokenizer` needs convert_tokens_to_ids /
+    convert_ids_to_tokens. Returns the list of strings."""
+    if length is None:
+        length = model.data_config["max_seq_length"]
+    start_id = tokenizer.convert_tokens_to_ids(start_token)
+    sampler = sample_sequence_batch if _sampler is None else _sampler
+    jobs = [(i, s) for i in range(len(dataset)) for s in range(n_samples)]
+    out = [None] * len(jobs)
+    for lo in range(0, len(jobs), rows_per_call):
+        chunk = jobs[lo:lo + rows_per_call]
+        starts = []
+        for i, _ in chunk:
+            item = {k: np.asarray(v) for k, v in dataset[i].items() if k != "rating"}
+            item["targets"] = np.asarray([start_id])
+            starts.append(item)
+        rows = sampler(model, starts, length, tokenizer, temperature, top_k, top_p, repitition_penalty, device,
+                       seed + lo)
+        for k, ids in enumerate(rows):
+            out[lo + k] = postprocess_tokens(tokenizer.convert_ids_to_tokens(ids))
+    if save_path is not None:
+        with open(save_path, "w", encoding="utf-8") as f:
+            for line in out:
+                f.write(line + "\n")
+    return out

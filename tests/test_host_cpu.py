@@ -170,3 +170,41 @@ def test_postprocess_tokens():
     assert postprocess_tokens(sent * 10 + ["x", "y"]) == "，".join(["ab"] * 10)
     assert postprocess_tokens(sent * 2 + ["[SEP]", "z"]) == "ab，ab"
     assert postprocess_tokens(sent) == "ab"
+
+
+def test_generate_samples_front_end_packs_and_orders_rows(tmp_path):
+    """src/generate.py:203-244 restated over the batched decoder: n_samples lines per item, dataset
+    order, every run started from [#START#], rows packed rows_per_call at a time."""
+    import numpy as np
+    from mmtg_b200.generate import generate_samples
+
+    vocab = ["[PAD]", "[#START#]", "[#EOS#]", "a", "b", "[SEP]"]
+
+    class Tok:
+        def convert_tokens_to_ids(self, t):
+            return vocab.index(t)
+
+        def convert_ids_to_tokens(self, ids):
+            return [vocab[i] for i in ids]
+
+    class Model:
+        data_config = {"max_seq_length": 7}
+
+    calls = []
+
+    def fake_sampler(model, starts, length, tokenizer, temperature, top_k, top_p, rep, device, seed):
+        calls.append((len(starts), length, seed))
+        rows = []
+        for s in starts:
+            assert s["targets"].tolist() == [1] and "rating" not in s
+            tag = 3 + int(s["topic_ids"][0]) % 2  # 'a' for even items, 'b' for odd ones
+            rows.append([1, tag, tag, 2, 1, tag, 2, 5, 0])
+        return rows
+
+    data = [{"topic_ids": np.array([i]), "rating": np.array(3)} for i in range(5)]
+    path = tmp_path / "samples.txt"
+    out = generate_samples(Model(), data, Tok(), n_samples=3, rows_per_call=4, save_path=str(path),
+                           _sampler=fake_sampler)
+    assert len(out) == 15 and [c[0] for c in calls] == [4, 4, 4, 3] and all(c[1] == 7 for c in calls)
+    assert out[:3] == ["aa，a"] * 3 and out[3:6] == ["bb，b"] * 3
+    assert path.read_text(encoding="utf-8").splitlines() == out
