@@ -169,6 +169,67 @@ def gpu_eager_step_time(batch_size, reps, dev, autocast):
     return float(np.median(ts))
 
 
+def run_decode(args, rank, local_rank):
+    """BASELINE.json configs[3]: greedy / top-k KV-cached generation, batch 64, 220 positions, 1 GPU
+    (generation does not shard: N > 1 = replicas only, rank 0 reports its own replica). One step =
+    one whole generation call through the public surface (host arrays in, token lists out)."""
+    if rank != 0:
+        return
+    from mmtg_b200 import _lib, synth
+    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200 import generate as G
+    from mmtg_b200.generate import sample_sequence_batch
+    from mmtg_b200.model import MMTG
+    B, LENGTH = 64, 220
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    model = MMTG(model_cfgs, data_config(), 13317, train_flag=False, token_table=synth.make_token_table())
+    model.load_state_dict(synth.make_state_dict(0))
+    model.to(dev)
+    batch = synth.make_batch(B, seed=1234)
+    starts = {k: v for k, v in batch.items() if k != "rating"}
+    starts["targets"] = np.ones((B, 1), np.int64)
+    presets = {"greedy": dict(temperature=1.0, top_k=1, top_p=0.0, repitition_penalty=1.0),
+               "topk10_p0.7": dict(temperature=1.1, top_k=10, top_p=0.7, repitition_penalty=1.5)}
+    W, K = max(args.warmup, 3), max(1, min(args.steps, 20))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    res = {}
+    for name, kw in presets.items():
+        for _ in range(W):
+            sample_sequence_batch(model, starts, LENGTH, device=str(dev), **kw)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count() + G.replayed_launches
+        t0 = time.perf_counter()
+        for i in range(K):
+            sample_sequence_batch(model, starts, LENGTH, device=str(dev), seed=i, **kw)
+        torch.cuda.synchronize()
+        res[name] = ((time.perf_counter() - t0) / K, (_lib.launch_count() + G.replayed_launches - l0) // K)
+    clocks = sampler.summary()
+    pk, pk_src = peaks()
+    sec, launches = res["greedy"]
+    # algorithmic bytes (SURVEY §8d): 193.2 MB of bf16 weights per position + 36,864 B of K/V per cached key and row
+    gbytes = (LENGTH * 193.2e6 + sum(36864.0 * (15 + j) for j in range(LENGTH)) * B) / 1e9
+    h2d = sum(np.asarray(v).nbytes for v in starts.values())
+    line = {
+        "metric": "decode tokens/s", "value": B * LENGTH / sec, "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "MMTG KV-cached greedy generation, batch 64, 220 positions, 1 GPU (BASELINE.json configs[3]); "
+                               "one step = one sample_sequence_batch call (prefill + 219 decoded positions, CUDA-graph replay)",
+                   "batch": B, "length": LENGTH, "l2": "per-position working set (193 MB weights + KV) exceeds L2"},
+        "e2e": {"value": B * LENGTH / sec, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": B * (LENGTH + 1) * 4,
+                "note": "the public call takes host arrays and returns host token lists: value == e2e"},
+        "gpu_launches": launches * K, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": gbytes / sec, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": gbytes / sec / pk["hbm_gbs"], "traffic": None,
+                     "kernel": "decode_mega_kernel (one persistent launch per position); algorithmic bytes = weights + KV per position",
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_src})"},
+        "topk_preset_tokens_per_s": B * LENGTH / res["topk10_p0.7"][0],
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -198,6 +259,10 @@ def main():
     ap.add_argument("--impl", default="mmtg_b200")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "decode"],
+                    help="train: BASELINE.json configs[1]/[2]/[4]; decode: configs[3] (KV-cached generation, 1 GPU)")
+    ap.add_argument("--max-sent-length", type=int, default=20,
+                    help="tokens per lyric sentence (20 = the reference's L = 236; configs[4] sweeps 40/60/98)")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="GPT-2 embd/resid/attn dropout of the training forward (reference default 0.1)")
     args = ap.parse_args()
@@ -206,6 +271,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "decode":
+        run_decode(args, rank, local_rank)
         return
 
     import torch.distributed as dist
@@ -226,17 +294,20 @@ def main():
     lib = _lib.lib()
 
     B = args.batch
+    dcfg = data_config(max_sent_length=args.max_sent_length)
+    L = dcfg["topic_prompt_length"] + dcfg["max_seq_length"] + 1
+    gflop_per_sample = {236: 140.2, 436: 263.6, 636: 391.4, 1016: 646.4}.get(L, 140.2 * L / 236.0)
     table = synth.make_token_table()
-    model = MMTG(model_cfgs, data_config(), 13317, train_flag=True, token_table=table)
+    model = MMTG(model_cfgs, dcfg, 13317, train_flag=True, token_table=table)
     model.load_state_dict(synth.make_state_dict(0))  # identical replicas on every rank
     model.set_dropout(args.dropout, args.dropout, args.dropout)
     model.set_dropout_seed(0x5EED + 7919 * rank)  # independent masks per data-parallel rank
     model.to(dev)
     if world > 1:
         model.grad_sync = GradSync()
-    crit = MyLoss(data_config(), model_cfgs)
+    crit = MyLoss(dcfg, model_cfgs)
     opt = FusedAdamW(model, lr=1e-5, max_grad_norm=1.0)
-    host = synth.batch_to_torch(synth.make_batch(B, seed=1234 + rank))
+    host = synth.batch_to_torch(synth.make_batch(B, seed=1234 + rank, data_config=dcfg))
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
@@ -340,7 +411,7 @@ def main():
     peak = pk["bf16_tflops_sustained"]
     # dominant kernel: the tcgen05 GEMM on the 7552x3072x768-FLOP shape family (c_fc forward, its
     # dgrad pair and the two 768x3072 wgrads: 84 of the 186 GEMM launches, ~55 % of GEMM time)
-    dom_flops = 2.0 * (B * 236) * 3072 * 768
+    dom_flops = 2.0 * (B * L) * 3072 * 768
     dom_ms, dom_n = 0.0, 0
     try:
         import csv as _csv
@@ -366,8 +437,8 @@ def main():
             "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "MMTG train step (fwd + MyLoss stage 3 + 0.2*KL, bwd, clip 1.0, AdamW) bf16 GEMMs / fp32 master+residual, batch 32 per GPU, L=236, V=13317 (BASELINE.json configs[1]); GPT-2 embd/resid/attn dropout p=%g (fused counter-based masks)" % args.dropout,
-                       "global_batch": global_batch, "seq_len": 236,
+            "config": {"workload": "MMTG train step (fwd + MyLoss stage 3 + 0.2*KL, bwd, clip 1.0, AdamW) bf16 GEMMs / fp32 master+residual, batch %d per GPU, L=%d, V=13317 (BASELINE.json configs[%d]); GPT-2 embd/resid/attn dropout p=%g (fused counter-based masks)" % (B, L, 1 if L == 236 else 4, args.dropout),
+                       "global_batch": global_batch, "seq_len": L,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "launch": "cuda_graph" if use_graph else "eager",
                        "l2": "working set (~3 GB activations/step) exceeds L2; 256 MB flush before profiled steps"},
@@ -377,12 +448,12 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "gemm_bf16_tcgen05_kernel, 2*7552*3072*768 FLOP per launch (c_fc fwd, its dgrads, the 768x3072 wgrads); CUDA events per launch in 2 eagerly launched steps",
+                         "kernel": f"gemm_bf16_tcgen05_kernel, 2*{B * L}*3072*768 FLOP per launch (c_fc fwd, its dgrads, the 768x3072 wgrads); CUDA events per launch in 2 eagerly launched steps",
                          "launches_per_step": dom_n // PROF_STEPS if dom_n else None,
                          "avg_launch_us": 1e3 * dom_ms / dom_n if dom_n else None,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk_src}; kernel timed inside a long step)",
                          "all_gemm_launches_tflops": all_gemm_tflops,
-                         "step_model_flops_frac": (value / world) * TRAIN_GFLOP_PER_SAMPLE / 1e3 / peak},
+                         "step_model_flops_frac": (value / world) * gflop_per_sample / 1e3 / peak},
             "breakdown": classes,
         }
         if world == 1 and not args.no_cpu_baseline:

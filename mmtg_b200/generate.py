@@ -71,6 +71,10 @@ def returned_length(length, sent_len):
     return i_last + 1
 
 
+# kernels launched through CUDA-graph replays (they bypass the library's launch counter)
+replayed_launches = 0
+
+
 class _DecodeSession:
     """Per-(batch, length, sampling preset) decode state kept on the model: KV-cache workspace,
     token / step-index / logits buffers and the captured CUDA graph of one decode step, so
@@ -195,7 +199,9 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
     graphed = use_cuda_graph and not return_step_logits
     if graphed and ses.graph is None and remaining > 2:
         for _ in range(2):  # eager warm-up (kernel attributes, descriptor cache), then capture
+            l0 = _lib.launch_count()
             one_step()
+            ses.launches_per_step = _lib.launch_count() - l0
         remaining -= 2
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
@@ -206,8 +212,10 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
         torch.cuda.current_stream().wait_stream(side)
         ses.graph = graph
     if graphed and ses.graph is not None:
+        global replayed_launches
         for _ in range(remaining):
             ses.graph.replay()
+        replayed_launches += remaining * getattr(ses, "launches_per_step", 0)
     else:
         for _ in range(remaining):
             one_step()
