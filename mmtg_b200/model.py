@@ -570,7 +570,10 @@ class MMTG(nn.Module):
 
     def _seed_tensor(self, device):
         if self._drop_seed is None or self._drop_seed.device != device:
-            self._drop_seed = torch.full((1,), self._drop_seed_init, dtype=torch.int64, device=device)
+            seed = self._drop_seed_init
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                seed += 7919 * torch.distributed.get_rank()  # independent masks per data-parallel rank
+            self._drop_seed = torch.full((1,), seed, dtype=torch.int64, device=device)
         return self._drop_seed
 
     def _c_model(self, d, device, train=False):
