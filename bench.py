@@ -211,6 +211,12 @@ def run_decode(args, rank, local_rank):
     # algorithmic bytes: 193.2 MB of bf16 weights per position + 36,864 B of K/V per cached key and row
     gbytes = (LENGTH * 193.2e6 + sum(36864.0 * (15 + j) for j in range(LENGTH)) * B) / 1e9
     h2d = sum(np.asarray(v).nbytes for v in starts.values())
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_decode_mega_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]  # one launch at position ~165 (ncu --set full)
+    except Exception:
+        pass
     line = {
         "metric": "decode tokens/s", "value": B * LENGTH / sec, "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -222,7 +228,7 @@ def run_decode(args, rank, local_rank):
                 "note": "the public call takes host arrays and returns host token lists: value == e2e"},
         "gpu_launches": launches * K, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": gbytes / sec, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": gbytes / sec / pk["hbm_gbs"], "traffic": None,
+                     "frac": gbytes / sec / pk["hbm_gbs"], "traffic": traffic,
                      "kernel": "decode_mega_kernel (one persistent launch per position); algorithmic bytes = weights + KV per position",
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_src})"},
         "topk_preset_tokens_per_s": B * LENGTH / res["topk10_p0.7"][0],
