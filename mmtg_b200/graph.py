@@ -46,12 +46,18 @@ class GraphedTrainStep:
             self.step, self.total, _, _ = model.fused_forward_loss(self.static, stage, alpha)
         pool = self.g_fwd.pool()
         self.nstage = self.step.dims.NL + 2
-        self.g_stage = []
-        for s in range(self.nstage):
+        # backward stages per captured segment: 1 = an all-reduce can start after every block;
+        # larger groups trade overlap granularity for fewer graph launches / stream hand-offs
+        # (measured ms/step at 2 GPUs: 9.43 / 9.30 / 9.20 for 1 / 2 / 4; at 8 GPUs 9.72 / 9.63 for 2 / 4)
+        import os
+        group = max(1, int(os.environ.get("MMTG_DDP_STAGE_GROUP", "4")))
+        self.g_stage = []  # (graph, first stage, one-past-last stage)
+        for s0 in range(0, self.nstage, group):
+            s1 = min(self.nstage, s0 + group)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
-                model.backward_stages(self.step, s, s + 1)
-            self.g_stage.append(g)
+                model.backward_stages(self.step, s0, s1)
+            self.g_stage.append((g, s0, s1))
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=pool, stream=self.cap_stream):
             optimizer.step()
@@ -101,9 +107,10 @@ class GraphedTrainStep:
             self.graph.replay()
             return self.total
         self.g_fwd.replay()
-        for s, g in enumerate(self.g_stage):
+        for g, s0, s1 in self.g_stage:
             g.replay()
-            self.sync.after_stage(self.model, s, self.nstage)
+            for s in range(s0, s1):
+                self.sync.after_stage(self.model, s, self.nstage)
         self.sync.finish(self.model)
         self.g_opt.replay()
         return self.total

@@ -1,7 +1,3 @@
 run() { echo "== $1"; env $1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 30 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'])"; }
-run "X=1"
-run "MMTG_GEMM_CTAS=140"
-run "MMTG_GEMM_CTAS=132"
-run "NCCL_MAX_CTAS=8"
-run "NCCL_MAX_CTAS=8 MMTG_GEMM_CTAS=140"
-run "NCCL_MAX_CTAS=4 MMTG_GEMM_CTAS=144"
+run "MMTG_DDP_STAGE_GROUP=2"
+run "MMTG_DDP_STAGE_GROUP=4"
