@@ -115,7 +115,8 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_train_step_time(batch_size, reps, threads):
-    """Restated reference train step (src/train.py:188-193) on the CPU oracle; returns s/step."""
+    """Restated reference train step (src/train.py:188-197: forward, MyLoss + alpha*KL, backward,
+    clip_grad_norm_(1.0), AdamW step) on the CPU oracle; returns s/step."""
     from mmtg_b200 import synth
     from mmtg_b200.configs import data_config
     from oracle import mmtg_oracle as O
@@ -123,16 +124,18 @@ def cpu_train_step_time(batch_size, reps, threads):
     table = torch.from_numpy(synth.make_token_table())
     sd = synth.make_state_dict(0)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "decoder.gpt2.lm_head.weight"}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-5, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0)
     params["decoder.gpt2.lm_head.weight"] = params["decoder.gpt2.transformer.wte.weight"]
     batch = synth.batch_to_torch(synth.make_batch(batch_size, seed=1234))
     ts = []
     for i in range(reps + 1):
-        for p in params.values():
-            p.grad = None
         t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
         hf, kl, logits = O.mmtg_forward(params, table, batch, data_config(), True)
         total = O.my_loss(logits, batch["targets"], batch["rating"], STAGE).mean() + ALPHA * kl.mean()
         total.backward()
+        torch.nn.utils.clip_grad_norm_(opt.param_groups[0]["params"], 1.0)
+        opt.step()
         if i > 0:  # first repetition is the warm-up
             ts.append(time.perf_counter() - t0)
     return float(np.median(ts))
@@ -248,9 +251,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "train samples/s", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": reps, "warmup": 1, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "MMTG train step fwd+bwd+curriculum negative loss, CPU fp32, bounded sample batch 2 (configs[1] shape per sample)"},
+        "data": "synthetic", "config": {"workload": "MMTG train step (fwd + MyLoss stage 3 + 0.2*KL, bwd, clip 1.0, AdamW), L=236, V=13317 (BASELINE.json configs[1]) -- reference algorithm (oracle port) on the host cores, fp32, bounded sample: batch 2 per step"},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{reps} timed steps of batch {bs} (L=236) after 1 warm-up, oracle/mmtg_oracle.py fwd+MyLoss+KL+autograd bwd"},
+                         "sample": f"{reps} timed steps of batch {bs} (L=236) after 1 warm-up, oracle/mmtg_oracle.py fwd+MyLoss+KL+autograd bwd+clip+AdamW"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -488,7 +491,7 @@ def main():
             threads = os.cpu_count() or 1
             sec = cpu_train_step_time(2, 3, threads)
             line["cpu_baseline"] = {"value": 2 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
-                                    "sample": "3 timed steps of batch 2 (L=236) after 1 warm-up, oracle/mmtg_oracle.py fwd+MyLoss+KL+autograd bwd, fp32"}
+                                    "sample": "3 timed steps of batch 2 (L=236) after 1 warm-up, oracle/mmtg_oracle.py fwd+MyLoss+KL+autograd bwd+clip+AdamW, fp32"}
             try:  # second reported baseline: the oracle in PyTorch eager on this GPU (forward+backward only)
                 bs = 32
                 line["torch_eager_gpu_baseline"] = {
