@@ -236,7 +236,8 @@ int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void* workspace
 /* device pointers into the workspace that the loss path reads/writes */
 float* mmtg_ws_lse(const mmtg_dims* dims, void* workspace);          /* [B*L] row log-sum-exp */
 void* mmtg_ws_dlogits_bf16(const mmtg_dims* dims, void* workspace);  /* [B*L, Vp] bf16 */
-/* Backward stages: 0 = lm_head + ln_f, 1..NL = blocks NL-1..0, NL+1 = projector/embedding/encoder.
+/* Backward stages: 0 = lm_head + ln_f, 1..NL = blocks NL-1..0, NL+1 = embeddings + projector,
+ * NL+2 = multi-modal attention + encoder (NL+3 stages in all).
  * Runs stages [stage_begin, stage_end). dlogits come from mmtg_ws_dlogits_bf16 (write them, or
  * convert an fp32 [B*L, V] gradient with mmtg_dlogits_from_f32, before stage 0).
  * g_kl: device scalar d(total)/d(kl) or null (= 0). */

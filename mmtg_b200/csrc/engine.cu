@@ -458,7 +458,7 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
   Ws w;
   carve(d, (uint8_t*)workspace, &w);
   MMTG_CHECK_ARG((int64_t)w.bytes <= workspace_bytes, "workspace too small");
-  MMTG_CHECK_ARG(stage_begin >= 0 && stage_end <= d.NL + 2 && stage_begin <= stage_end, "bad stage range");
+  MMTG_CHECK_ARG(stage_begin >= 0 && stage_end <= d.NL + 3 && stage_begin <= stage_end, "bad stage range");
   cudaStream_t st = (cudaStream_t)stream;
   const float* P = m->params;
   const bf16* W = (const bf16*)m->params_bf16;
@@ -538,7 +538,7 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_in, L.mean1, L.rstd1, P + lo.ln1_w, w.dh, 1, G + lo.ln1_w,
                              G + lo.ln1_b, g_out, l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, st,
                              &d_in));
-    } else {
+    } else if (stage == d.NL + 1) {
       // ---------------- embeddings + projector ----------------
       MMTG_TRY(posadd_bwd(w.dh, G + o.wpe, B, d.L, E, st));
       MMTG_TRY(typeadd_bwd(w.dh, b->type_ids, G + o.wte, M, E, st));
@@ -549,6 +549,9 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(w.dp1, He, w.emb16, Dw, G + o.proj1_w, Dw, He, Dw, M, s2, wg); }));
       MMTG_TRY(Gemm(w.dp1, He, false, W + o.proj1_w, Dw, true, M, Dw, He).out_bf16(w.dE, Dw).run(st));
       MMTG_TRY(embed_bwd(w.dE, w.dctx16, nullptr, B, d.P, d.T, S, d.two_sent, Dw, st));
+    } else {
+      // (a stage of its own: the projector / wpe / ln_f / tied-wte gradients above are final, so a
+      // data-parallel caller can all-reduce that 50 MB bucket while the encoder side runs)
       // ---------------- beta gate ----------------
       MMTG_TRY(colsum(w.dctx16, 1, Dw, nullptr, 0, G + o.beta_out_b, SB, Dw, st));
       MMTG_TRY(Gemm(w.dctx16, Dw, false, W + o.beta_out_w, He, true, SB, He, Dw).out_bf16(w.do16, He).run(st));

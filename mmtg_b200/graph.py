@@ -45,15 +45,18 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.g_fwd, stream=self.cap_stream):
             self.step, self.total, _, _ = model.fused_forward_loss(self.static, stage, alpha)
         pool = self.g_fwd.pool()
-        self.nstage = self.step.dims.NL + 2
+        self.nstage = self.step.dims.NL + 3
         # backward stages per captured segment: 1 = an all-reduce can start after every block;
         # larger groups trade overlap granularity for fewer graph launches / stream hand-offs
         # (measured ms/step at 2 GPUs: 9.43 / 9.30 / 9.20 for 1 / 2 / 4; at 8 GPUs 9.72 / 9.63 for 2 / 4)
         import os
         group = max(1, int(os.environ.get("MMTG_DDP_STAGE_GROUP", "4")))
         self.g_stage = []  # (graph, first stage, one-past-last stage)
-        for s0 in range(0, self.nstage, group):
-            s1 = min(self.nstage, s0 + group)
+        # the encoder-side stage is always a segment of its own: the projector / wte bucket that is
+        # final before it is all-reduced while it runs
+        bounds = [(s0, min(self.nstage - 1, s0 + group)) for s0 in range(0, self.nstage - 1, group)]
+        bounds.append((self.nstage - 1, self.nstage))
+        for s0, s1 in bounds:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
                 model.backward_stages(self.step, s0, s1)

@@ -298,6 +298,12 @@ class MMTG(nn.Module):
     def tail_bucket(self):
         return self._layers_flat_end, self._flat_numel
 
+    def tail_buckets(self):
+        """The tail split where the backward splits it: (projector, wpe, ln_f, tied wte) are final
+        after stage NL+1, (encoder, multi-modal attention) after stage NL+2."""
+        mid = self._layout["decoder.projector_layer1.weight"][0]
+        return (mid, self._flat_numel), (self._layers_flat_end, mid)
+
     def reset_parameters(self):
         """Reference init: xavier/orthogonal encoder (src/model.py:83-88), nn.Linear defaults,
         HF GPT-2 normal(0, 0.02) (residual projections scaled by 1/sqrt(2 n_layer))."""
@@ -535,10 +541,10 @@ class MMTG(nn.Module):
         return step, total, loss, kl
 
     def backward_stages(self, step, s0=0, s1=None):
-        """Run backward stages [s0, s1) of `step` (0 = lm_head, 1..NL = blocks NL-1..0, NL+1 =
+        """Run backward stages [s0, s1) of `step` (0 = lm_head, 1..NL = blocks NL-1..0, NL+1 = embeddings/projector, NL+2 =
         embeddings/encoder) with d(total)/d(kl) = alpha; gradients accumulate into param.grad."""
         d = step.dims
-        s1 = d.NL + 2 if s1 is None else s1
+        s1 = d.NL + 3 if s1 is None else s1
         _lib.check(_lib.lib().mmtg_train_backward(C.byref(step.cm), C.byref(step.cb), C.c_void_p(step.ws.data_ptr()),
                                                   C.c_int64(step.ws.numel()), C.c_void_p(self._alpha_buf.data_ptr()),
                                                   s0, s1, C.c_void_p(_lib.stream_ptr())), "mmtg_train_backward")
@@ -714,7 +720,7 @@ def _run_backward(step, gkl):
     lib = _lib.lib()
     st = C.c_void_p(_lib.stream_ptr())
     wsp = C.c_void_p(step.ws.data_ptr())
-    nstage = d.NL + 2
+    nstage = d.NL + 3
     sync = mdl.grad_sync
     if sync is None:
         _lib.check(lib.mmtg_train_backward(C.byref(step.cm), C.byref(step.cb), wsp, C.c_int64(step.ws.numel()),

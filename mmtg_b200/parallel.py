@@ -1,7 +1,7 @@
 """Data-parallel gradient exchange (replaces torch.nn.DataParallel, src/train.py:112-114).
 
 One process per GPU, identical replicas, batch sharded by rank. The backward engine runs in
-stages (lm_head, block 11 .. block 0, embeddings/encoder); as soon as a stage has produced the
+stages (lm_head, block 11 .. block 0, embeddings + projector, encoder side); as soon as a stage has produced the
 gradients of one contiguous bucket of the flat gradient buffer (a GPT-2 block = 7.1 M params =
 28 MB fp32) that bucket is all-reduced (NCCL over NVLink/NVSwitch through torch.distributed) on a
 side stream while the next stage computes. There is no parameter broadcast and no logits gather.
@@ -46,12 +46,15 @@ class GradSync:
 
     def after_stage(self, model, stage, nstage):
         G = model._flat[2]
-        nl = nstage - 2
+        nl = nstage - 3
         if 1 <= stage <= nl:
             lo, hi = model.layer_bucket(nl - stage)
             self._reduce(G[lo:hi])
-        elif stage == nstage - 1:
-            lo, hi = model.tail_bucket()
+        elif stage == nl + 1:  # projector, wpe, ln_f, tied wte: reduced while the encoder side runs
+            lo, hi = model.tail_buckets()[0]
+            self._reduce(G[lo:hi])
+        elif stage == nl + 2:  # encoder + multi-modal attention
+            lo, hi = model.tail_buckets()[1]
             self._reduce(G[lo:hi])
 
     def finish(self, model):

@@ -24,6 +24,11 @@ class _FakeModel:
     def tail_bucket(self):
         return self.nl * self.per, self.nl * self.per + self.tail
 
+    def tail_buckets(self):
+        lo, hi = self.tail_bucket()
+        mid = lo + self.tail // 3
+        return (mid, hi), (lo, mid)
+
 
 def _worker(rank, world, port):
     sys.path.insert(0, ROOT)
@@ -33,7 +38,7 @@ def _worker(rank, world, port):
     from mmtg_b200.parallel import GradSync
     m = _FakeModel(nl=4, per_layer=1000, tail=333, rank=rank)
     sync = GradSync()
-    nstage = m.nl + 2
+    nstage = m.nl + 3
     touched = torch.zeros_like(m._flat[2])
     for s in range(nstage):
         before = m._flat[2].clone()
@@ -52,8 +57,8 @@ def _worker(rank, world, port):
     m2 = _FakeModel(nl=2, per_layer=10, tail=7, rank=rank)
     m2._flat[2].fill_(scale * (rank + 1))  # per-rank mean gradient (rank + 1), pre-scaled
     s2 = GradSync(average=False)
-    for s in range(m2.nl + 2):
-        s2.after_stage(m2, s, m2.nl + 2)
+    for s in range(m2.nl + 3):
+        s2.after_stage(m2, s, m2.nl + 3)
     want = (3 * 1 + 5 * 2) / 8.0  # gradient of the mean over the 8 concatenated rows
     assert torch.allclose(m2._flat[2], torch.full_like(m2._flat[2], want))
     dist.destroy_process_group()
