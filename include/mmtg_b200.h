@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MMTG_ABI_VERSION 1
+#define MMTG_ABI_VERSION 2
 
 const char* mmtg_last_error(void);
 int mmtg_abi_version(void);

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
-    assert lib.mmtg_abi_version() == 1
+    assert lib.mmtg_abi_version() == 2
     lib.mmtg_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.mmtg_last_error(), bytes)
 
