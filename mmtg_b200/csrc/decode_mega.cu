@@ -89,7 +89,7 @@ __device__ __forceinline__ void warp_row_stats(const float* __restrict__ src, in
   const float4* xr = reinterpret_cast<const float4*>(src + (long long)row * E);
   float4 v[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) v[i] = xr[l + i * 32];
+  for (int i = 0; i < 6; ++i) v[i] = __ldcg(xr + l + i * 32);  // written by other CTAs in this launch: L2, never .nc / L1
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 6; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
@@ -151,8 +151,8 @@ __device__ __forceinline__ void stage_a(const void* __restrict__ A, long long ld
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
       const uint4* s4 = reinterpret_cast<const uint4*>((const bf16*)A + (long long)r * lda + k0 + t * 64 + cq * 16);
-      u[t][0] = s4[0];
-      u[t][1] = s4[1];
+      u[t][0] = __ldcg(s4);
+      u[t][1] = __ldcg(s4 + 1);
     }
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
@@ -166,12 +166,12 @@ __device__ __forceinline__ void stage_a(const void* __restrict__ A, long long ld
   for (int t = 0; t < KT; ++t) {
     const float4* s4 = reinterpret_cast<const float4*>((const float*)A + (long long)r * lda + k0 + t * 64 + cq * 16);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[t][i] = s4[i];
+    for (int i = 0; i < 4; ++i) v[t][i] = __ldcg(s4 + i);
   }
   float mean = 0.f, rstd = 0.f;
   if (MODE == A_GELU) {
-    mean = stats[r * 2];
-    rstd = stats[r * 2 + 1];
+    mean = __ldcg(stats + r * 2);
+    rstd = __ldcg(stats + r * 2 + 1);
   }
 #pragma unroll
   for (int t = 0; t < KT; ++t) {
@@ -312,7 +312,7 @@ __device__ __forceinline__ void attn_warp(const MegaParams& p, const float* __re
     attn_issue(p, layer, u, 0, wbuf, bars);
     if (nch > 1) attn_issue(p, layer, u, 1, wbuf, bars);
   }
-  const float mean = p.w.row_stats[b * 2], rstd = p.w.row_stats[b * 2 + 1];
+  const float mean = __ldcg(p.w.row_stats + b * 2), rstd = __ldcg(p.w.row_stats + b * 2 + 1);
   const float* acc_row = p.w.qkv_acc + (long long)b * 3 * E + h * 64;
   const float* cs = fv + h * 64;          // cs_attn
   const float* bq = fv + 3 * E + h * 64;  // b'_attn
@@ -323,7 +323,7 @@ __device__ __forceinline__ void attn_warp(const MegaParams& p, const float* __re
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       const int col = kk * 16 + hh * 8 + 2 * g4;
-      const float2 a = *reinterpret_cast<const float2*>(acc_row + col);
+      const float2 a = __ldcg(reinterpret_cast<const float2*>(acc_row + col));
       const float2 c2 = __ldg(reinterpret_cast<const float2*>(cs + col));
       const float2 b2 = __ldg(reinterpret_cast<const float2*>(bq + col));
       const float q0 = (rstd * (a.x - mean * c2.x) + b2.x) * 0.125f;
@@ -339,7 +339,7 @@ __device__ __forceinline__ void attn_warp(const MegaParams& p, const float* __re
   if (ks < 2) {
     const int col = (ks + 1) * E + part * 8;
     float x[8];
-    const float4 a0 = *reinterpret_cast<const float4*>(acc_row + col), a1 = *reinterpret_cast<const float4*>(acc_row + col + 4);
+    const float4 a0 = __ldcg(reinterpret_cast<const float4*>(acc_row + col)), a1 = __ldcg(reinterpret_cast<const float4*>(acc_row + col + 4));
     const float4 c0 = __ldg(reinterpret_cast<const float4*>(cs + col)), c1 = __ldg(reinterpret_cast<const float4*>(cs + col + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bq + col)), b1 = __ldg(reinterpret_cast<const float4*>(bq + col + 4));
     x[0] = rstd * (a0.x - mean * c0.x) + b0.x; x[1] = rstd * (a0.y - mean * c0.y) + b0.y;
@@ -492,7 +492,7 @@ __device__ __forceinline__ void stage_head(const float* __restrict__ h, int B, i
   const uint32_t o0 = ((c0) ^ (r & 7)) << 4, o1 = ((c0 + 1) ^ (r & 7)) << 4;
   const bool valid = r < B;
   const float* hr = h + (long long)(valid ? r : 0) * E;
-  const float shift = hr[0];
+  const float shift = __ldcg(hr);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
   for (int t0 = 0; t0 < E / 64; t0 += 6) {
@@ -501,7 +501,7 @@ __device__ __forceinline__ void stage_head(const float* __restrict__ h, int B, i
     for (int t = 0; t < 6; ++t) {
       const float4* s4 = reinterpret_cast<const float4*>(hr + (t0 + t) * 64 + cq * 16);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[t][i] = s4[i];
+      for (int i = 0; i < 4; ++i) v[t][i] = __ldcg(s4 + i);
     }
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
@@ -671,7 +671,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
       for (long long i = sid * 4; i < (long long)B * 4 * E; i += sth * 4)
         *reinterpret_cast<float4*>(p.w.u_acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int i = (int)sid * 4; i < B * E; i += (int)sth * 4) {
-        float4 v = *reinterpret_cast<const float4*>(h + i);
+        float4 v = __ldcg(reinterpret_cast<const float4*>(h + i));
         const float4 bb = __ldg(reinterpret_cast<const float4*>(p.P + lo.proj_b + i % E));
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
         *reinterpret_cast<float4*>(p.w.h2 + i) = v;
@@ -707,7 +707,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
     // ---- D: u_acc += bf16(h2) W'_fc ; side jobs: LN2 stats of h2, h_next = h2 + b_proj2 ----
     if (warp == 7 && cta < B) warp_row_stats(p.w.h2, cta, E, statsD);
     for (int i = (int)gtid * 4; i < B * E; i += (int)gthreads * 4) {
-      float4 v = *reinterpret_cast<const float4*>(p.w.h2 + i);
+      float4 v = __ldcg(reinterpret_cast<const float4*>(p.w.h2 + i));
       const float4 bb = __ldg(reinterpret_cast<const float4*>(p.P + lo.proj2_b + i % E));
       v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
       *reinterpret_cast<float4*>(hn + i) = v;
