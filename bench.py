@@ -209,15 +209,15 @@ def run_decode(args, rank, local_rank):
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / K, (_lib.launch_count() + G.replayed_launches - l0) // K
 
-    fused_default = os.environ.get("MMTG_DECODE_MEGA", "0") == "1"
+    fused_default = os.environ.get("MMTG_DECODE_MEGA", "1") != "0"
     res = {name: timed(kw) for name, kw in presets.items()}
     other = None
-    if not fused_default:  # informational: the opt-in fused persistent-kernel step on the same workload
-        os.environ["MMTG_DECODE_MEGA"] = "1"
+    if fused_default:  # informational: the bit-reproducible per-op decode step on the same workload
+        os.environ["MMTG_DECODE_MEGA"] = "0"
         try:
             other = timed(presets["greedy"])
         finally:
-            os.environ["MMTG_DECODE_MEGA"] = "0"
+            os.environ["MMTG_DECODE_MEGA"] = "1"
     clocks = sampler.summary()
     pk, pk_src = peaks()
     sec, launches = res["greedy"]
@@ -248,12 +248,11 @@ def run_decode(args, rank, local_rank):
                                + "; algorithmic bytes = weights + KV per position",
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_src})"},
         "topk_preset_tokens_per_s": B * LENGTH / res["topk10_p0.7"][0],
-        "decode_step": "fused persistent kernel (MMTG_DECODE_MEGA=1)" if fused_default else "per-op launches (default)",
+        "decode_step": "fused persistent kernel (default)" if fused_default else "per-op launches (MMTG_DECODE_MEGA=0)",
     }
     if other is not None:
-        line["fused_step_opt_in"] = {"tokens_per_s": B * LENGTH / other[0], "ms_per_step": other[0] * 1e3,
-                                     "note": "MMTG_DECODE_MEGA=1: one persistent kernel per position; opt-in until its "
-                                             "intermittent run-to-run greedy-id mismatch is resolved (DESIGN.md §8)"}
+        line["per_op_step"] = {"tokens_per_s": B * LENGTH / other[0], "ms_per_step": other[0] * 1e3,
+                               "note": "MMTG_DECODE_MEGA=0: ~90 launches per position, bit-reproducible (no atomics)"}
     print(json.dumps(line), flush=True)
 
 
