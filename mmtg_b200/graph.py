@@ -18,6 +18,17 @@ from __future__ import annotations
 import torch
 
 
+def segment_bounds(nstage: int, group: int):
+    """[s0, s1) backward-stage ranges of the captured graph segments of a data-parallel step:
+    `group` stages per segment, except that the last stage (the encoder side) is always a segment
+    of its own — the projector / tied-wte gradient bucket that is final before it is all-reduced
+    while it runs."""
+    group = max(1, int(group))
+    bounds = [(s0, min(nstage - 1, s0 + group)) for s0 in range(0, nstage - 1, group)]
+    bounds.append((nstage - 1, nstage))
+    return bounds
+
+
 class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, example_batch, alpha=0.2, stage=3, warmup=3):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
@@ -52,11 +63,7 @@ class GraphedTrainStep:
         import os
         group = max(1, int(os.environ.get("MMTG_DDP_STAGE_GROUP", "4")))
         self.g_stage = []  # (graph, first stage, one-past-last stage)
-        # the encoder-side stage is always a segment of its own: the projector / wte bucket that is
-        # final before it is all-reduced while it runs
-        bounds = [(s0, min(self.nstage - 1, s0 + group)) for s0 in range(0, self.nstage - 1, group)]
-        bounds.append((self.nstage - 1, self.nstage))
-        for s0, s1 in bounds:
+        for s0, s1 in segment_bounds(self.nstage, group):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
                 model.backward_stages(self.step, s0, s1)

@@ -208,3 +208,15 @@ def test_generate_samples_front_end_packs_and_orders_rows(tmp_path):
     assert len(out) == 15 and [c[0] for c in calls] == [4, 4, 4, 3] and all(c[1] == 7 for c in calls)
     assert out[:3] == ["aa，a"] * 3 and out[3:6] == ["bb，b"] * 3
     assert path.read_text(encoding="utf-8").splitlines() == out
+
+
+def test_ddp_graph_segments_cover_every_stage_once():
+    from mmtg_b200.graph import segment_bounds
+    for nstage in (15, 5, 3):
+        for group in (1, 2, 4, 7, 100):
+            b = segment_bounds(nstage, group)
+            flat = [s for s0, s1 in b for s in range(s0, s1)]
+            assert flat == list(range(nstage)), (nstage, group, b)
+            assert b[-1] == (nstage - 1, nstage)  # the encoder-side stage is its own segment
+            assert all(s1 - s0 <= max(1, group) for s0, s1 in b)
+    assert segment_bounds(15, 4) == [(0, 4), (4, 8), (8, 12), (12, 14), (14, 15)]
