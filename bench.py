@@ -2,6 +2,7 @@
 """bench.py — MMTG hot-path benchmark (contract: see the task statement / DESIGN.md §Measurement).
 
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload train|decode]
+                  [--max-sent-length 20|40|60|98] [--batch B] [--dropout P]
 
 One "step" = one pass of the training hot path over one synthetic batch of 32 samples per GPU:
 MMTG.forward + MyLoss + 0.2*KL, backward (with the bucketed NCCL gradient all-reduce when N > 1),
@@ -14,6 +15,10 @@ global-norm clip and the AdamW update (restated src/train.py:188-197). Metric: t
   roofline     : tensor bound for the dominant kernel (the tcgen05 GEMM), from per-launch CUDA
                  events recorded by the library in extra, separately run, profiled steps
   cpu_baseline : the CPU oracle's train step on the host cores (bounded sample)
+
+`--workload decode` = BASELINE.json configs[3] (KV-cached generation, batch 64, 220 positions, 1 GPU):
+metric decode tokens/s, HBM roofline. `--max-sent-length` > 20 = the extended-length runs of configs[4].
+`torch_eager_gpu_baseline` (N = 1) = the oracle run by PyTorch eager on the same GPU, a second reported baseline.
 
 `--impl reference` times the reference's own CPU implementation of the path (the oracle port:
 /root/reference does not exist on the GPU box) on the host cores and prints the same line.
