@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MMTG_ABI_VERSION 2
+#define MMTG_ABI_VERSION 3
 
 const char* mmtg_last_error(void);
 int mmtg_abi_version(void);
@@ -215,7 +215,9 @@ typedef struct mmtg_model {
    * changes *drop_seed between steps (mmtg_dropout_next_seed). All p = 0 or NULL seed: off. */
   const uint64_t* drop_seed;
   float p_embd, p_resid, p_attn;
-  int32_t _pad_drop;
+  /* rows of token_table: a token id outside [0, table_rows) makes the embedding kernels trap
+   * (the reference raises KeyError on an id missing from its dict, src/model.py:256,263) */
+  int32_t table_rows;
 } mmtg_model;
 
 typedef struct mmtg_batch {
@@ -291,7 +293,10 @@ int mmtg_decode_step_fused(const mmtg_model* m, int32_t Lmax, void* decode_works
 int mmtg_decode_set_trace(uint64_t* dev_buf);
 /* ban_specials: set ids 1, 2, 100, 102 to -inf (src/generate.py:133-136).
  * seed_dev (optional, device): overrides `seed`, so a captured launch can be re-seeded.
- * dbg_probs (optional): [B, 1024, 2] (kept token id, probability) of the filtered distribution */
+ * top_k in [1, 1024]: descending selection; top_k == 0: pure nucleus (top_p > 0, no survivor cap)
+ * or plain softmax sampling (top_p == 0).
+ * dbg_probs (optional, test hook): [B, V] probabilities of the filtered distribution (0 = filtered
+ * out); when given, the PAD-continuation shortcut is skipped so the distribution is always produced */
 int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_ld, int32_t* j_ptr,
                      int32_t B, int32_t V, int32_t sent_len, float temperature, int32_t top_k,
                      float top_p, float rep_penalty, uint64_t seed, const uint64_t* seed_dev,
@@ -307,7 +312,7 @@ int mmtg_grad_norm_sq(const float* grads, int64_t n, float* partial_ws, int32_t 
 /* lr_dev / step_dev (optional, device): learning rate and 0-based step counter kept on the device
  * (the counter is bumped after the update) so the call can be replayed from a CUDA graph. */
 int mmtg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                    void* params_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                    void* params_bf16, int64_t n, float lr, double beta1, double beta2, float eps,
                     float weight_decay, int32_t step, int32_t correct_bias, const float* normsq,
                     float max_norm, const float* lr_dev, int32_t* step_dev, void* stream);
 

@@ -62,7 +62,7 @@ def lib() -> C.CDLL:
         _lib.mmtg_decode_workspace_bytes.restype = C.c_int64
         _lib.mmtg_ws_lse.restype = C.c_void_p
         _lib.mmtg_ws_dlogits_bf16.restype = C.c_void_p
-        if _lib.mmtg_abi_version() != 2:
+        if _lib.mmtg_abi_version() != 3:
             raise MMTGError("libmmtg_b200.so ABI version mismatch")
     return _lib
 

@@ -527,7 +527,7 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
   }
   dim3 grid(cdiv(L, BQ), B * NH);
   constexpr int BWD_SMEM = 6 * BQ * HD * 2 + 4 * BQ * 4;  // 6 bf16 tiles + 4 x 64 floats
-  static bool attr_set = false;
+  MMTG_PER_DEVICE_FLAG(attr_set);
   if (!attr_set) {
     MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));

@@ -298,7 +298,7 @@ int attn_fwd_tc(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B,
   CUtensorMap tm;
   MMTG_CHECK_ARG(L <= 1024, "tcgen05 attention forward handles L <= 1024");
   MMTG_TRY(make_tmap_bf16_2d(&tm, qkv, (uint64_t)3 * E, (uint64_t)B * L, (uint64_t)3 * E, 64, 128));
-  static bool attr_set = false;
+  MMTG_PER_DEVICE_FLAG(attr_set);
   if (!attr_set) {
     MMTG_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
@@ -621,7 +621,7 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float
   CUtensorMap tm_qkv, tm_do;
   MMTG_TRY(make_tmap_bf16_2d(&tm_qkv, qkv, (uint64_t)3 * E, (uint64_t)B * L, (uint64_t)3 * E, 64, 128));
   MMTG_TRY(make_tmap_bf16_2d(&tm_do, dout, (uint64_t)E, (uint64_t)B * L, (uint64_t)E, 64, 128));
-  static bool attr_set = false;
+  MMTG_PER_DEVICE_FLAG(attr_set);
   if (!attr_set) {
     MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_TOTAL));
     attr_set = true;

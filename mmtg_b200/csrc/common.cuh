@@ -53,6 +53,12 @@ const char* get_last_error();
   } while (0)
 
 int num_sms();  // cached SM count of the current device
+int current_device_index();  // cudaGetDevice() clamped to [0, 63]
+// One-time CUDA state that lives PER DEVICE (function attributes, __constant__ uploads): the flag
+// is indexed by the current device, so a process that touches a second GPU initialises it too.
+#define MMTG_PER_DEVICE_FLAG(name)          \
+  static bool name##_by_dev[64] = {false};  \
+  bool& name = name##_by_dev[::mmtg::current_device_index()]
 
 // Optional launch timing (see core.cu). classes: 0 GEMM, 1 attention, 2 row/reduction kernels.
 int prof_begin(int cls, double flops, double bytes, cudaStream_t st);

@@ -21,6 +21,12 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return g_err; }
 
+int current_device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

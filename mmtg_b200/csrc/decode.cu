@@ -87,11 +87,15 @@ decode_prep_kernel(const int* __restrict__ gen, int gen_ld, const int* __restric
                    const float* __restrict__ table, const float* __restrict__ ctx,
                    bf16* __restrict__ emb16, int* __restrict__ types, int* __restrict__ posidx,
                    int* __restrict__ keymask, int B, int P, int S, int sent_len, int n_sent, int D,
-                   int Lmax, unsigned int* __restrict__ barrier) {
+                   int Lmax, unsigned int* __restrict__ barrier, int table_rows) {
   const int b = blockIdx.x;
   if (b == 0 && threadIdx.x == 0) *barrier = 0u;  // the megakernel's grid barrier starts from zero
   const int j = *j_ptr;
   const int tok = gen[b * gen_ld + j];
+  if ((unsigned)tok >= (unsigned)table_rows) {
+    if (threadIdx.x == 0) printf("mmtg: token id %d (row %d, step %d) is outside the token table [0, %d)\n", tok, b, j, table_rows);
+    __trap();
+  }
   if (threadIdx.x == 0) {
     int ty;
     const int r = (j + 1) % sent_len;
@@ -276,7 +280,85 @@ __device__ ArgMax block_argmax(const float* s, int V, ArgMax* red) {
   return r;
 }
 
-constexpr int MAX_SURV = 1024;
+constexpr int MAX_SURV = 1024;  // top-k survivors kept in shared memory (pure top-p has no cap)
+
+// order-preserving float -> uint32 key (larger float <=> larger key; -inf is the smallest real key)
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// block-wide sum, result broadcast to every thread (`red`: >= 32 floats of shared memory)
+__device__ float block_sum(float a, float* red) {
+  a = warp_sum(a);
+  if (lane_id() == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// Multinomial draw over {c : s[c] >= thr} with weights exp(s[c] - mx); u01 in [0, 1). Threads own
+// contiguous chunks, so the prefix order is the vocabulary order (any fixed order is a valid
+// inverse-CDF draw). Returns the picked id to every thread.
+__device__ int block_draw(const float* s, int V, uint32_t thr_key, float mx, float u01, float* red, int* pick_slot) {
+  const int per = (V + blockDim.x - 1) / blockDim.x;
+  const int c0 = threadIdx.x * per, c1 = min(V, c0 + per);
+  float local = 0.f;
+  for (int c = c0; c < c1; ++c)
+    if (float_key(s[c]) >= thr_key && s[c] != -INFINITY) local += __expf(s[c] - mx);
+  // inclusive scan of the per-thread sums: warp scan + scan of the warp totals
+  float incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane_id() >= o) incl += t;
+  }
+  if (lane_id() == 31) red[threadIdx.x >> 5] = incl;
+  if (threadIdx.x == 0) *pick_slot = -1;
+  __syncthreads();
+  float base = 0.f, total = 0.f;
+  const int nw = blockDim.x >> 5;
+  for (int w = 0; w < nw; ++w) {
+    if (w < (int)(threadIdx.x >> 5)) base += red[w];
+    total += red[w];
+  }
+  const float u = u01 * total;
+  const float lo = base + incl - local, hi = base + incl;
+  if (local > 0.f && u >= lo && u < hi) {
+    float c2 = lo;
+    int pick = -1;
+    for (int c = c0; c < c1; ++c)
+      if (float_key(s[c]) >= thr_key && s[c] != -INFINITY) {
+        c2 += __expf(s[c] - mx);
+        pick = c;
+        if (u < c2) break;
+      }
+    *pick_slot = pick;  // intervals are disjoint: at most one writer
+  }
+  __syncthreads();
+  int r = *pick_slot;
+  if (r < 0) {  // u fell on a rounding gap at the very top: take the last kept id
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int c = V - 1; c >= 0; --c)
+        if (float_key(s[c]) >= thr_key && s[c] != -INFINITY) {
+          *pick_slot = c;
+          break;
+        }
+    }
+    __syncthreads();
+    r = *pick_slot;
+  }
+  __syncthreads();
+  return r;
+}
 
 __global__ void __launch_bounds__(1024)
 sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ gen, int gen_ld,
@@ -286,6 +368,7 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restri
   if (seed_dev) seed = seed_dev[0];  // device-side seed: the launch stays CUDA-graph replayable
   extern __shared__ float s[];  // [V] working logits
   __shared__ ArgMax red[32];
+  __shared__ float fred[32];
   __shared__ float sv[MAX_SURV];
   __shared__ int si[MAX_SURV];
   __shared__ int s_n;
@@ -295,7 +378,7 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restri
   int next = -1;
   if (i > 0 && (i + 2) % sent_len == 0) next = 2;        // forced [#EOS#]   (generate.py:118-120)
   else if (i > 0 && (i + 2) % sent_len == 1) next = 1;   // forced [#START#] (generate.py:121-123)
-  else if (g[i] == 0) next = 0;                          // PAD continuation (generate.py:137-138)
+  else if (g[i] == 0 && !dbg_probs) next = 0;            // PAD continuation (generate.py:137-138)
   if (next < 0) {
     const float* z = logits + (long long)b * ld;
     for (int c = threadIdx.x; c < V; c += blockDim.x) s[c] = z[c];
@@ -315,107 +398,106 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restri
       s[1] = -INFINITY; s[2] = -INFINITY; s[100] = -INFINITY; s[102] = -INFINITY;
     }
     __syncthreads();
-    // full-vocabulary softmax normaliser is only needed for pure top-p (top_k == 0)
-    float lse_all = 0.f;
-    if (top_k <= 0 && top_p > 0.f) {
-      ArgMax m = block_argmax(s, V, red);
-      float a = 0.f;
-      for (int c = threadIdx.x; c < V; c += blockDim.x) a += __expf(s[c] - m.v);
-      a = warp_sum(a);
-      if (lane_id() == 0) sv[threadIdx.x >> 5] = a;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += sv[w2];
-        sv[0] = m.v + logf(t);
-      }
-      __syncthreads();
-      lse_all = sv[0];
-      __syncthreads();
-    }
-    // descending selection of survivors
-    int n = 0;
-    float cum = 0.f, kth = -INFINITY;
+    const uint64_t rbits = splitmix64(seed ^ splitmix64(((uint64_t)b << 32) | (uint32_t)i));
+    const float u01 = (float)(rbits >> 40) * (1.0f / 16777216.0f);
     const int kk = top_k > 0 ? min(top_k, V) : 0;
-    while (n < MAX_SURV) {
+    if (kk == 0) {
+      // ---- no top-k: pure nucleus (top_p > 0) or plain softmax sampling (top_p == 0) ----
+      // generate.py:81-92 keeps, in descending order, every token whose PRECEDING cumulative
+      // probability is <= p (the first always). With F(v) = sum_{z_j > v} softmax(z)_j that set is
+      // {c : F(z_c) <= p} = {c : z_c >= t*}, t* the smallest float with F(t*) <= p: found by
+      // bisection over the order-preserving integer keys (32 block reductions), no sort and no
+      // survivor cap. Exact ties at the threshold are kept or dropped together.
       const ArgMax m = block_argmax(s, V, red);
-      if (m.v == -INFINITY) break;
-      if (kk > 0) {
+      uint32_t thr = 0u;  // key threshold: keep {c : key(s[c]) >= thr}, -inf excluded
+      float zsum = 0.f;
+      {
+        float a = 0.f;
+        for (int c = threadIdx.x; c < V; c += blockDim.x) a += __expf(s[c] - m.v);
+        zsum = block_sum(a, fred);
+      }
+      if (top_p > 0.f) {
+        uint32_t lo = 0u, hi = float_key(m.v);  // F(key(max)) = 0 <= p: hi always satisfies
+        while (lo < hi) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          float a = 0.f;
+          for (int c = threadIdx.x; c < V; c += blockDim.x)
+            if (float_key(s[c]) > mid) a += __expf(s[c] - m.v);
+          const float F = block_sum(a, fred) / zsum;
+          if (F <= top_p) hi = mid;
+          else lo = mid + 1;
+        }
+        thr = lo;  // smallest key with F <= p
+      }
+      const int pick = block_draw(s, V, thr, m.v, u01, fred, &s_n);
+      if (dbg_probs) {  // test hook: dense probabilities of the filtered distribution
+        float a = 0.f;
+        for (int c = threadIdx.x; c < V; c += blockDim.x)
+          if (float_key(s[c]) >= thr && s[c] != -INFINITY) a += __expf(s[c] - m.v);
+        const float kept = block_sum(a, fred);
+        float* d = dbg_probs + (long long)b * V;
+        for (int c = threadIdx.x; c < V; c += blockDim.x)
+          d[c] = (float_key(s[c]) >= thr && s[c] != -INFINITY) ? __expf(s[c] - m.v) / kept : 0.f;
+      }
+      next = pick;
+    } else {
+      // ---- top-k (<= 1024): descending selection of the survivors, then nucleus over them ----
+      int n = 0;
+      float kth = -INFINITY;
+      while (n < MAX_SURV) {
+        const ArgMax m = block_argmax(s, V, red);
+        if (m.v == -INFINITY) break;
         if (n >= kk && m.v < kth) break;  // beyond the k-th value (ties at the k-th are kept)
         if (n == kk - 1) kth = m.v;
-      } else if (top_p > 0.f) {
-        // pure nucleus: stop once the PRECEDING cumulative probability exceeds p
-        if (n > 0 && cum > top_p) break;
-        cum += __expf(m.v - lse_all);
-      } else {
-        break;  // neither filter (k = 0, p = 0): full-vocabulary multinomial below
+        if (threadIdx.x == 0) {
+          sv[n] = m.v;
+          si[n] = m.i;
+          s[m.i] = -INFINITY;
+        }
+        __syncthreads();
+        ++n;
+      }
+      if (dbg_probs) {
+        float* d = dbg_probs + (long long)b * V;
+        for (int c = threadIdx.x; c < V; c += blockDim.x) d[c] = 0.f;
+        __syncthreads();
       }
       if (threadIdx.x == 0) {
-        sv[n] = m.v;
-        si[n] = m.i;
-        s[m.i] = -INFINITY;
-      }
-      __syncthreads();
-      ++n;
-    }
-    if (n == 0 && kk == 0 && top_p <= 0.f) {
-      // plain softmax sampling over the whole (banned-id filtered) vocabulary
-      const ArgMax m = block_argmax(s, V, red);
-      if (threadIdx.x == 0) {
+        int keep = n;
+        if (top_p > 0.f) {
+          // nucleus over the top-k survivors (softmax over survivors only: the rest are -inf)
+          float t = 0.f;
+          for (int c = 0; c < n; ++c) t += __expf(sv[c] - sv[0]);
+          float c2 = 0.f;
+          keep = 0;
+          for (int c = 0; c < n; ++c) {
+            if (c > 0 && c2 > top_p) break;
+            c2 += __expf(sv[c] - sv[0]) / t;
+            ++keep;
+          }
+        }
+        // multinomial over the kept survivors
         float t = 0.f;
-        for (int c = 0; c < V; ++c) t += __expf(s[c] - m.v);
-        const uint64_t r = splitmix64(seed ^ splitmix64(((uint64_t)b << 32) | (uint32_t)i));
-        const float u = (float)(r >> 40) * (1.0f / 16777216.0f) * t;
+        for (int c = 0; c < keep; ++c) t += __expf(sv[c] - sv[0]);
+        const float u = u01 * t;
         float c2 = 0.f;
-        int pick = m.i;
-        for (int c = 0; c < V; ++c) {
-          c2 += __expf(s[c] - m.v);
+        int pick = keep > 0 ? si[keep - 1] : 0;
+        for (int c = 0; c < keep; ++c) {
+          c2 += __expf(sv[c] - sv[0]);
           if (u < c2) {
-            pick = c;
+            pick = si[c];
             break;
           }
         }
         s_n = pick;
-      }
-    } else if (threadIdx.x == 0) {
-      int keep = n;
-      if (kk > 0 && top_p > 0.f) {
-        // nucleus over the top-k survivors (softmax over survivors only: the rest are -inf)
-        float t = 0.f;
-        for (int c = 0; c < n; ++c) t += __expf(sv[c] - sv[0]);
-        float c2 = 0.f;
-        keep = 0;
-        for (int c = 0; c < n; ++c) {
-          if (c > 0 && c2 > top_p) break;
-          c2 += __expf(sv[c] - sv[0]) / t;
-          ++keep;
+        if (dbg_probs) {
+          float* d = dbg_probs + (long long)b * V;
+          for (int c = 0; c < keep; ++c) d[si[c]] = __expf(sv[c] - sv[0]) / t;
         }
       }
-      // multinomial over the kept survivors
-      float t = 0.f;
-      for (int c = 0; c < keep; ++c) t += __expf(sv[c] - sv[0]);
-      const uint64_t r = splitmix64(seed ^ splitmix64(((uint64_t)b << 32) | (uint32_t)i));
-      const float u = (float)(r >> 40) * (1.0f / 16777216.0f) * t;
-      float c2 = 0.f;
-      int pick = keep > 0 ? si[keep - 1] : 0;
-      for (int c = 0; c < keep; ++c) {
-        c2 += __expf(sv[c] - sv[0]);
-        if (u < c2) {
-          pick = si[c];
-          break;
-        }
-      }
-      s_n = pick;
-      if (dbg_probs) {  // test hook: kept ids and their probabilities
-        float* d = dbg_probs + (long long)b * 2 * MAX_SURV;
-        for (int c = 0; c < MAX_SURV; ++c) {
-          d[2 * c] = c < keep ? (float)si[c] : -1.f;
-          d[2 * c + 1] = c < keep ? __expf(sv[c] - sv[0]) / t : 0.f;
-        }
-      }
+      __syncthreads();
+      next = s_n;
     }
-    __syncthreads();
-    next = s_n;
   }
   if (threadIdx.x == 0) g[i + 1] = next;
   // the shared step index is advanced by a separate 1-thread kernel (advance_kernel): doing it
@@ -490,7 +572,8 @@ int decode_step_impl(const mmtg_model* m, int32_t Lmax, void* decode_ws, const i
   const int B = d.B, E = d.E, He = d.He, Dw = d.Dw;
   const float eps = 1e-5f;
   decode_prep_kernel<<<B, 256, 0, st>>>(gen, gen_ld, j_ptr, m->token_table, w.ctx, w.emb16, w.types,
-                                        w.posidx, w.keymask, B, d.P, d.S, sent_len, n_sent, Dw, Lmax, w.mega.barrier);
+                                        w.posidx, w.keymask, B, d.P, d.S, sent_len, n_sent, Dw, Lmax, w.mega.barrier,
+                                        m->table_rows);
   MMTG_LAUNCH_OK();
   count_launch();
   auto gemm = [&](const bf16* A, long long lda, const bf16* Bm, long long ldb, bool b_mn, int N, int K) {
@@ -571,8 +654,9 @@ extern "C" int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, i
                                 uint64_t seed, const uint64_t* seed_dev, int32_t ban_specials,
                                 float* dbg_probs, void* stream) {
   MMTG_CHECK_ARG(logits && gen && j_ptr && B > 0 && V > 102 && temperature > 0.f, "bad sampler args");
-  MMTG_CHECK_ARG(top_k <= MAX_SURV, "top_k > %d not supported", MAX_SURV);
-  static bool attr_set = false;
+  MMTG_CHECK_ARG(top_k >= 0 && top_k <= MAX_SURV, "top_k must be in [0, %d] (0 = no top-k filter)", MAX_SURV);
+  MMTG_CHECK_ARG(top_p >= 0.f, "top_p must be >= 0");
+  MMTG_PER_DEVICE_FLAG(attr_set);
   const int smem = V * 4;
   if (!attr_set) {
     MMTG_CUDA_OK(cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

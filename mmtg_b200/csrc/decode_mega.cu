@@ -846,7 +846,7 @@ int decode_mega_launch(const mmtg_model* m, int Lmax, const MegaBufs& bufs, cons
   const mmtg_dims& d = m->dims;
   MMTG_CHECK_ARG(d.B <= 64 && d.E == 768 && d.NH * 64 == d.E && Lmax <= 1024,
                  "decode megakernel: unsupported shape (B=%d E=%d Lmax=%d)", d.B, d.E, Lmax);
-  static bool attr_set = false;
+  MMTG_PER_DEVICE_FLAG(attr_set);
   if (!attr_set) {
     MMTG_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
     attr_set = true;

@@ -244,7 +244,7 @@ colsum_kernel(const void* __restrict__ x_, long long ld, bf16* __restrict__ copy
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const float* __restrict__ table, const int* __restrict__ topic_ids,
                  const int* __restrict__ input_ids, const float* __restrict__ ctx,
-                 bf16* __restrict__ out, int B, int P, int T, int S, int two_sent, int D) {
+                 bf16* __restrict__ out, int B, int P, int T, int S, int two_sent, int D, int table_rows) {
   const int row = blockIdx.x;
   const int L = P + T;
   const int b = row / L, p = row - b * L;
@@ -255,6 +255,11 @@ embed_fwd_kernel(const float* __restrict__ table, const int* __restrict__ topic_
     const int j = p - P;
     id = input_ids[b * T + j];
     if (j / two_sent < S) k = j / two_sent;
+  }
+  if ((unsigned)id >= (unsigned)table_rows) {  // the reference's dict lookup raises KeyError here
+    if (threadIdx.x == 0)
+      printf("mmtg: token id %d at (row %d, position %d) is outside the token table [0, %d)\n", id, b, p, table_rows);
+    __trap();
   }
   const float* trow = table + (long long)id * D;
   const float* crow = k >= 0 ? ctx + ((long long)k * B + b) * D : nullptr;
@@ -405,10 +410,12 @@ int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc,
 }
 
 int embed_fwd(const float* table, const int* topic_ids, const int* input_ids, const float* ctx,
-              bf16* out, int B, int P, int T, int S, int two_sent, int D, cudaStream_t st) {
+              bf16* out, int B, int P, int T, int S, int two_sent, int D, int table_rows, cudaStream_t st) {
   MMTG_CHECK_ARG(D % 8 == 0, "embedding width must be a multiple of 8");
+  MMTG_CHECK_ARG(table_rows > 0, "token table row count missing (mmtg_model.table_rows)");
   ProfScope prof(2, 0, (double)B * (P + T) * D * 6, st);
-  embed_fwd_kernel<<<B * (P + T), 256, 0, st>>>(table, topic_ids, input_ids, ctx, out, B, P, T, S, two_sent, D);
+  embed_fwd_kernel<<<B * (P + T), 256, 0, st>>>(table, topic_ids, input_ids, ctx, out, B, P, T, S, two_sent, D,
+                                                table_rows);
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;
@@ -475,7 +482,8 @@ extern "C" int mmtg_embed_fwd(const float* table, const int32_t* topic_ids, cons
                               const float* ctx, void* out_bf16, int32_t B, int32_t P, int32_t T,
                               int32_t S, int32_t two_sent, int32_t D, void* stream) {
   MMTG_CHECK_ARG(table && topic_ids && input_ids && out_bf16, "bad embed args");
-  return embed_fwd(table, topic_ids, input_ids, ctx, (bf16*)out_bf16, B, P, T, S, two_sent, D, (cudaStream_t)stream);
+  return embed_fwd(table, topic_ids, input_ids, ctx, (bf16*)out_bf16, B, P, T, S, two_sent, D, 0x7fffffff,
+                   (cudaStream_t)stream);  // standalone op (tests): the caller vouches for the ids
 }
 extern "C" int mmtg_embed_bwd(const void* dE_bf16, void* dctx_bf16, float* dctx_f32, int32_t B, int32_t P,
                               int32_t T, int32_t S, int32_t two_sent, int32_t D, void* stream) {

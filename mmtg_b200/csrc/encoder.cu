@@ -317,11 +317,10 @@ beta_bwd_kernel(const float* __restrict__ topic, const float* __restrict__ img,
   for (int e = 0; e < PER; ++e) dtopic[(long long)b * H + l + 32 * e] = dx0[e];
 }
 
-bool g_prior_ready = false;
-
 }  // namespace
 
 static int ensure_prior() {
+  MMTG_PER_DEVICE_FLAG(g_prior_ready);  // c_prior is per-device __constant__ memory
   if (g_prior_ready) return 0;
   float t[AS * AS];
   for (int i = 0; i < AS; ++i) {

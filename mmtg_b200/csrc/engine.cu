@@ -365,7 +365,7 @@ extern "C" int mmtg_train_forward(const mmtg_model* m, const mmtg_batch* b, void
                .out_f32(w.ctx_out, Dw).bias(P + o.beta_out_b).run(st));
   // ---------------- decoder embedding + projector (src/model.py:253-281) ----------------
   MMTG_TRY(embed_fwd(m->token_table, b->topic_ids, b->targets, w.ctx_out, w.emb16, B, d.P, d.T, S,
-                     d.two_sent, Dw, st));
+                     d.two_sent, Dw, m->table_rows, st));
   MMTG_TRY(Gemm(w.emb16, Dw, false, W + o.proj1_w, Dw, false, M, He, Dw)
                .out_bf16(w.p1, He).bias(P + o.proj1_b).act(MMTG_ACT_TANH).run(st));
   {  // h0 = p1 W2^T + b2 + wpe[pos] + wte[type]   (HF modeling_gpt2.py:579-612)

@@ -725,7 +725,7 @@ template <int BN, uint32_t EPI, bool TWO>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        cudaStream_t st) {
   using C = GemmCfg<BN, TWO>;
-  static bool attr_set = false;
+  MMTG_PER_DEVICE_FLAG(attr_set);
   if (!attr_set) {
     MMTG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, TWO>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));

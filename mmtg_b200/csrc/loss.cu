@@ -69,9 +69,17 @@ __global__ void lse_combine_kernel(const float* __restrict__ part, float* __rest
   lse[row] = m + logf(s);
 }
 
+// Labels are vocabulary ids: anything outside [0, bound) — including torch's ignore_index -100,
+// which the reference path never produces (src/loss.py:62-71, no -100 anywhere) — traps instead
+// of reading outside the logits row.
 __device__ __forceinline__ int label_at(const int* topic_ids, const int* targets, int b, int pos,
-                                        int P, int T) {
-  return pos < P ? topic_ids[b * P + pos] : targets[b * T + (pos - P)];
+                                        int P, int T, int bound) {
+  const int lab = pos < P ? topic_ids[b * P + pos] : targets[b * T + (pos - P)];
+  if ((unsigned)lab >= (unsigned)bound) {
+    printf("mmtg: label %d at (row %d, position %d) is outside the vocabulary [0, %d)\n", lab, b, pos, bound);
+    __trap();
+  }
+  return lab;
 }
 
 // Per sample b: nll(b,t) = lse[b,t] - z[b,t,label(b,t+1)] for t in [0, L-2].
@@ -86,7 +94,7 @@ ce_reduce_kernel(const float* __restrict__ logits, long long ld, const float* __
   float a_hf = 0.f, a_ce = 0.f;
   for (int t = threadIdx.x; t < L - 1; t += 256) {
     if (t + 1 < P && topic_ids == nullptr) continue;  // generic MyLoss path: prompt labels unknown
-    const int lab = label_at(topic_ids, targets, b, t + 1, P, T);
+    const int lab = label_at(topic_ids, targets, b, t + 1, P, T, (int)ld);
     const long long row = (long long)b * L + t;
     const float nll = lse[row] - __ldg(logits + row * ld + lab);
     a_hf += nll;
@@ -173,7 +181,7 @@ ce_bwd_kernel(const float* __restrict__ logits, long long ld, const float* __res
     }
     return;
   }
-  const int lab = label_at(topic_ids, targets, b, t + 1, P, T);
+  const int lab = label_at(topic_ids, targets, b, t + 1, P, T, V);
   const float* z = logits + row * ld;
   const float l = lse[row];
   for (int c = threadIdx.x; c < ncols; c += 256) {

@@ -22,7 +22,7 @@ int cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
 int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc, float* out, int M,
            int N, cudaStream_t st);
 int embed_fwd(const float* table, const int* topic_ids, const int* input_ids, const float* ctx,
-              bf16* out, int B, int P, int T, int S, int two_sent, int D, cudaStream_t st);
+              bf16* out, int B, int P, int T, int S, int two_sent, int D, int table_rows, cudaStream_t st);
 int embed_bwd(const bf16* dE, bf16* dctx16, float* dctx32, int B, int P, int T, int S, int two_sent,
               int D, cudaStream_t st);
 int posadd_bwd(const float* dh, float* dwpe, int B, int L, int E, cudaStream_t st);

@@ -49,15 +49,20 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, flo
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, bf16* __restrict__ p16, long long n, float lr, float b1, float b2,
-             float eps, float wd, float step_size, const float* __restrict__ normsq, float max_norm,
-             const float* __restrict__ lr_dev, const int* __restrict__ step_dev, int correct_bias) {
+             float omb1, float omb2, float eps, float wd, float step_size, const float* __restrict__ normsq,
+             float max_norm, const float* __restrict__ lr_dev, const int* __restrict__ step_dev,
+             int correct_bias) {
+  // omb1 = 1 - beta1, omb2 = 1 - beta2 rounded ONCE from double on the host, as torch rounds the
+  // python scalars of `exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)`: 1.f - 0.999f is 1.3e-5 off
   if (lr_dev) lr = lr_dev[0];
   if (step_dev) {
     // device-side schedule state: the launch is replayable from a CUDA graph
     step_size = lr;
     if (correct_bias) {
       const float t = (float)(step_dev[0] + 1);
-      step_size = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+      // 1 - beta^t = -expm1(t log1p(-(1 - beta))): no cancellation at small t
+      const float bc1 = -expm1f(t * log1pf(-omb1)), bc2 = -expm1f(t * log1pf(-omb2));
+      step_size = lr * sqrtf(bc2) / bc1;
     }
   }
   float clip = 1.f;
@@ -75,8 +80,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float gr = gp[e] * clip;
-      mp[e] = b1 * mp[e] + (1.f - b1) * gr;
-      vp[e] = b2 * vp[e] + (1.f - b2) * gr * gr;
+      mp[e] = b1 * mp[e] + omb1 * gr;
+      vp[e] = b2 * vp[e] + omb2 * gr * gr;
       pp[e] -= step_size * mp[e] / (sqrtf(vp[e]) + eps);
       if (wd != 0.f) pp[e] -= lr * wd * pp[e];
     }
@@ -113,7 +118,7 @@ extern "C" int mmtg_grad_norm_sq(const float* grads, int64_t n, float* partial_w
 }
 
 extern "C" int mmtg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                               void* params_bf16, int64_t n, float lr, float beta1, float beta2,
+                               void* params_bf16, int64_t n, float lr, double beta1, double beta2,
                                float eps, float weight_decay, int32_t step, int32_t correct_bias,
                                const float* normsq, float max_norm, const float* lr_dev,
                                int32_t* step_dev, void* stream) {
@@ -122,14 +127,15 @@ extern "C" int mmtg_adamw_step(float* params, const float* grads, float* exp_avg
   MMTG_CHECK_ARG(!(lr_dev && !step_dev), "lr_dev requires step_dev (device-side schedule state)");
   float step_size = lr;
   if (correct_bias && !step_dev) {
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
     step_size = (float)((double)lr * sqrt(bc2) / bc1);
   }
   const int blocks = num_sms() * 8;
   ProfScope prof(2, 0, (double)n * 30.0, (cudaStream_t)stream);
   adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq,
-                                                          (bf16*)params_bf16, n, lr, beta1, beta2, eps,
+                                                          (bf16*)params_bf16, n, lr, (float)beta1, (float)beta2,
+                                                          (float)(1.0 - beta1), (float)(1.0 - beta2), eps,
                                                           weight_decay, step_size, normsq, max_norm,
                                                           lr_dev, step_dev, correct_bias);
   MMTG_LAUNCH_OK();

@@ -171,7 +171,7 @@ int skinny_gemm(const mmtg_gemm_args* a, cudaStream_t st) {
   MMTG_CHECK_ARG(cdiv(nk, ks) <= MAX_KB, "skinny GEMM: K=%d too large (max %d)", a->K, 8 * MAX_KB * 64);
   const int kb_per = cdiv(nk, ks);
   const int SMEM = 2 * kb_per * 64 * 64 * 2 + 64 * PART_PITCH * 4;
-  static bool attr_set = false;
+  MMTG_PER_DEVICE_FLAG(attr_set);
   if (!attr_set) {
     MMTG_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       2 * MAX_KB * 64 * 64 * 2 + 64 * PART_PITCH * 4));

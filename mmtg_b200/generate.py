@@ -26,32 +26,38 @@ _INT_KEYS = ("topic_ids", "tpw_attention_mask", "tpw_type_ids")
 
 def top_k_top_p_filtering(logits, top_k=0, top_p=0.0, filter_value=-float("Inf")):
     """src/generate.py:64-94 on the device sampler: returns `logits` with every token the
-    reference would filter set to `filter_value` (1-D logits; temperature 1, no penalty)."""
+    reference would filter set to `filter_value` (1-D logits; temperature 1, no penalty).
+    top_k = 0 with top_p > 0 is the pure nucleus filter (the function's defaults filter nothing)."""
     assert logits.dim() == 1
     if not logits.is_cuda:
         raise _lib.MMTGError("mmtg_b200.top_k_top_p_filtering runs on CUDA only")
     V = logits.numel()
-    kept, _ = _filtered_distribution(logits.detach().float().view(1, V), top_k, top_p, ban=False)
-    keep = torch.zeros(V, dtype=torch.bool, device=logits.device)
-    keep[kept[0][kept[0] >= 0].long()] = True
-    logits[~keep] = filter_value
+    probs = _filtered_distribution(logits.detach().float().view(1, V), top_k, top_p, ban=False)
+    finite = torch.isfinite(logits)
+    logits[(probs[0] <= 0) & finite] = filter_value
     return logits
 
 
-def _filtered_distribution(logits2d, top_k, top_p, temperature=1.0, ban=True):
-    """(kept ids [B, 1024] (-1 padded), probabilities [B, 1024]) of the sampler's distribution."""
+def _filtered_distribution(logits2d, top_k, top_p, temperature=1.0, ban=True, history=None, rep_penalty=1.0):
+    """Dense [B, V] probabilities of the sampler's filtered distribution (0 = filtered out).
+    `history`: optional [B, n] int token ids the repetition penalty is applied over."""
     Bn, V = logits2d.shape
     dev = logits2d.device
     z = logits2d.contiguous()
-    gen = torch.full((Bn, 4), 5, dtype=torch.int32, device=dev)  # dummy history, never PAD
-    j = torch.zeros(1, dtype=torch.int32, device=dev)
-    dbg = torch.empty(Bn, 1024, 2, device=dev)
+    if history is None:
+        gen = torch.full((Bn, 4), 5, dtype=torch.int32, device=dev)  # dummy history (penalty 1: unused)
+        j = torch.zeros(1, dtype=torch.int32, device=dev)
+    else:
+        h = torch.as_tensor(history, dtype=torch.int32, device=dev).view(Bn, -1)
+        gen = torch.cat([h, torch.zeros(Bn, 1, dtype=torch.int32, device=dev)], 1).contiguous()
+        j = torch.full((1,), h.shape[1] - 1, dtype=torch.int32, device=dev)
+    dbg = torch.empty(Bn, V, device=dev)
     _lib.check(_lib.lib().mmtg_sample_rows(C.c_void_p(z.data_ptr()), C.c_int64(z.stride(0)), C.c_void_p(gen.data_ptr()),
-                                           4, C.c_void_p(j.data_ptr()), Bn, V, 1 << 20, C.c_float(temperature),
-                                           int(top_k), C.c_float(top_p), C.c_float(1.0), C.c_uint64(0), None, int(ban),
+                                           gen.shape[1], C.c_void_p(j.data_ptr()), Bn, V, 1 << 20, C.c_float(temperature),
+                                           int(top_k), C.c_float(top_p), C.c_float(rep_penalty), C.c_uint64(0), None, int(ban),
                                            C.c_void_p(dbg.data_ptr()), C.c_void_p(_lib.stream_ptr())),
                "mmtg_sample_rows")
-    return dbg[..., 0], dbg[..., 1]
+    return dbg
 
 
 def _collate(start_inputs):

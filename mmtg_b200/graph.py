@@ -113,6 +113,8 @@ class GraphedTrainStep:
                 src = batch[k]
                 if src is not dst:
                     dst.copy_(src, non_blocking=True)
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()  # an LR scheduler's param_groups['lr'] -> the device copy the graph reads
         if self.sync is None:
             self.graph.replay()
             return self.total

@@ -34,17 +34,19 @@ class _FusedLoss(torch.autograd.Function):
                                       d.P, d.T, st), "mmtg_ce_reduce")
         _lib.check(lib.mmtg_negloss(_vp(ce.data_ptr()), _vp(ratings.data_ptr()), stage, _vp(loss.data_ptr()),
                                     _vp(coef.data_ptr()), d.B, st), "mmtg_negloss")
-        ctx.step, ctx.coef, ctx.targets, ctx.logits = step, coef, targets, logits
+        ctx.step = step  # holds the logits only weakly (model._Step): no cycle through this node
+        ctx.save_for_backward(logits, coef, targets)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         step, d = ctx.step, ctx.step.dims
+        logits, coef, targets = ctx.saved_tensors
         if step.serial != step.model._serial:
             raise _lib.MMTGError("loss.backward() after a newer forward(): activation workspace overwritten")
         g = g.detach().float().contiguous()
-        _lib.check(_lib.lib().mmtg_ce_bwd(_vp(ctx.logits.data_ptr()), C.c_int64(d.V), _vp(step.lse_ptr), None,
-                                          _vp(ctx.targets.data_ptr()), _vp(ctx.coef.data_ptr()),
+        _lib.check(_lib.lib().mmtg_ce_bwd(_vp(logits.data_ptr()), C.c_int64(d.V), _vp(step.lse_ptr), None,
+                                          _vp(targets.data_ptr()), _vp(coef.data_ptr()),
                                           _vp(g.data_ptr()), None, _vp(step.dlogits_ptr), 1, C.c_int64(d.Vp),
                                           d.B, d.L, d.P, d.T, d.V, _vp(_lib.stream_ptr())), "mmtg_ce_bwd")
         step.dlogits_ready = True

@@ -15,6 +15,7 @@ import json
 import math
 import os
 import pickle
+import weakref
 
 import numpy as np
 import torch
@@ -60,7 +61,7 @@ class Model(C.Structure):
     _fields_ = [("dims", Dims), ("off", ParamOffsets), ("params", C.c_void_p),
                 ("params_bf16", C.c_void_p), ("grads", C.c_void_p), ("token_table", C.c_void_p),
                 ("drop_seed", C.c_void_p), ("p_embd", C.c_float), ("p_resid", C.c_float),
-                ("p_attn", C.c_float), ("_pad_drop", C.c_int32)]
+                ("p_attn", C.c_float), ("table_rows", C.c_int32)]
 
 
 class Batch(C.Structure):
@@ -221,7 +222,7 @@ class MMTG(nn.Module):
         self.decoder = GPT2_Decoder(data_config, gpt2_config=gpt2_config, token_table=token_table)
         self.train_flag = train_flag
         self._flat = None       # (P, W16, G) flat buffers
-        self._flat_versions = None
+        self._w16_fresh = False  # True only right after FusedAdamW.step() (see _refresh_bf16)
         self._ws = {}           # workspace cache keyed by dims tuple
         self._serial = 0
         self._anchor = None
@@ -364,7 +365,7 @@ class MMTG(nn.Module):
                 p.data = view
                 p.grad = None
         self._flat = (P, W16, G)
-        self._flat_versions = None
+        self._w16_fresh = False
         self._grads_fresh = True
         self._named = named
         self._offsets = self._make_offsets()
@@ -402,14 +403,23 @@ class MMTG(nn.Module):
         return o
 
     def _refresh_bf16(self):
-        """Re-cast the bf16 shadow when any master weight changed (optimizer step, load_state_dict)."""
-        vers = tuple(p._version for p in self._named.values())
-        if vers != self._flat_versions:
-            P, W16, _ = self._flat
-            _lib.check(_lib.lib().mmtg_cast_bf16(C.c_void_p(P.data_ptr()), C.c_void_p(W16.data_ptr()),
-                                                 C.c_int64(P.numel()), C.c_void_p(_lib.stream_ptr())),
-                       "mmtg_cast_bf16")
-            self._flat_versions = vers
+        """Re-cast the bf16 weight shadow from the fp32 masters at EVERY forward, unless the one
+        writer that keeps the shadow coherent itself (FusedAdamW: its kernel stores the bf16 copy
+        next to the fp32 update) has marked it fresh since the previous forward. Tensor version
+        counters are NOT trusted: `p.data.add_()` (transformers.AdamW of the pinned 4.12.3, EMA,
+        clamping, manual copies) changes the masters without bumping them. One HBM-bound kernel
+        (436 MB read + 218 MB written, ~0.1 ms)."""
+        if self._w16_fresh:
+            self._w16_fresh = False  # consumed: whatever happens before the next forward is unknown
+            return
+        P, W16, _ = self._flat
+        _lib.check(_lib.lib().mmtg_cast_bf16(C.c_void_p(P.data_ptr()), C.c_void_p(W16.data_ptr()),
+                                             C.c_int64(P.numel()), C.c_void_p(_lib.stream_ptr())),
+                   "mmtg_cast_bf16")
+
+    def mark_bf16_shadow_fresh(self):
+        """Called by FusedAdamW.step(): the optimizer kernel has just rewritten the bf16 shadow."""
+        self._w16_fresh = True
 
     def _table(self, device):
         d = self.decoder
@@ -482,7 +492,6 @@ class MMTG(nn.Module):
         self._serial += 1
         step.serial = self._serial
         step.ws_serial_owner = self
-        step.logits = torch.empty(B, d.L, d.V, device=device, dtype=torch.float32)
         step.scalars = torch.zeros(4, device=device, dtype=torch.float32)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._named.values())
         if need_grad:
@@ -490,12 +499,15 @@ class MMTG(nn.Module):
                 self._anchor = torch.zeros((), device=device, requires_grad=True)
             hf, kl, logits, token = _MMTGFunction.apply(self._anchor, step)
             step.token = token
+            step.logits = logits  # weak (see _Step)
             logits._mmtg_step = step
             return hf, kl, logits
-        _run_forward(step)
-        step.logits._mmtg_step = step
+        logits = torch.empty(B, d.L, d.V, device=device, dtype=torch.float32)
+        _run_forward(step, logits)
+        step.logits = logits
+        logits._mmtg_step = step
         step.token = None
-        return step.scalars[0], step.scalars[1], step.logits
+        return step.scalars[0], step.scalars[1], logits
 
     # ------------------------------------------------------------------------------------------
     def fused_forward_loss(self, batch, stage, alpha=0.2, grad_scale=1.0):
@@ -587,7 +599,8 @@ class MMTG(nn.Module):
         m.dims, m.off = d, self._offsets
         P, W16, G = self._flat
         m.params, m.params_bf16, m.grads = P.data_ptr(), W16.data_ptr(), G.data_ptr()
-        m.token_table = self._table(device).data_ptr()
+        tab = self._table(device)
+        m.token_table, m.table_rows = tab.data_ptr(), tab.shape[0]
         if train and self.dropout_active():
             m.drop_seed = self._seed_tensor(device).data_ptr()
             m.p_embd, m.p_resid, m.p_attn = self._drop_p
@@ -604,6 +617,7 @@ class MMTG(nn.Module):
             if k.endswith((".attn.bias", ".attn.masked_bias")):
                 continue
             sd[k] = v
+        self._w16_fresh = False  # the masters change underneath the bf16 shadow
         return super().load_state_dict(sd, strict=strict, **kw)
 
 
@@ -625,8 +639,22 @@ def _inference_types_and_mask(input_ids, tpw_type_ids, tpw_att_mask, data_config
 
 
 class _Step:
-    """Everything one forward produced that backward / the fused loss needs."""
+    """Everything one forward produced that backward / the fused loss needs.
+
+    Ownership is one-directional: the logits tensor owns its step (`logits._mmtg_step`), the step
+    only holds a WEAK reference back (`step.logits`), and the autograd nodes keep the tensors they
+    need through `save_for_backward`. There is no reference cycle, so the 402 MB logits buffer of
+    a B = 32 step is released by reference counting as soon as the caller drops it."""
     dlogits_ready = False
+    _logits_ref = None
+
+    @property
+    def logits(self):
+        return self._logits_ref() if self._logits_ref is not None else None
+
+    @logits.setter
+    def logits(self, t):
+        self._logits_ref = weakref.ref(t) if t is not None else None
 
 
 def _c_batch(step):
@@ -637,16 +665,16 @@ def _c_batch(step):
     return b
 
 
-def _run_forward(step):
+def _run_forward(step, logits):
     mdl = step.model
-    device = step.logits.device
+    device = logits.device
     m, b = mdl._c_model(step.dims, device, train=True), _c_batch(step)
     step.cm, step.cb = m, b
     if m.drop_seed:  # fresh masks for this step; backward regenerates them from the same seed
         _lib.check(_lib.lib().mmtg_dropout_next_seed(C.c_void_p(m.drop_seed), C.c_void_p(_lib.stream_ptr())),
                    "mmtg_dropout_next_seed")
     rc = _lib.lib().mmtg_train_forward(C.byref(m), C.byref(b), C.c_void_p(step.ws.data_ptr()),
-                                       C.c_int64(step.ws.numel()), C.c_void_p(step.logits.data_ptr()),
+                                       C.c_int64(step.ws.numel()), C.c_void_p(logits.data_ptr()),
                                        C.c_void_p(step.scalars.data_ptr()), 1, C.c_void_p(_lib.stream_ptr()))
     _lib.check(rc, "mmtg_train_forward")
     lib = _lib.lib()
@@ -660,10 +688,13 @@ class _MMTGFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, step):
         ctx.set_materialize_grads(False)
-        ctx.step = step
-        _run_forward(step)
-        token = torch.zeros((), device=step.logits.device)
-        return step.scalars[0].clone(), step.scalars[1].clone(), step.logits, token
+        ctx.step = step  # step -> logits is a weak reference: no cycle through the node
+        d = step.dims
+        logits = torch.empty(d.B, d.L, d.V, device=anchor.device, dtype=torch.float32)
+        _run_forward(step, logits)
+        token = torch.zeros((), device=logits.device)
+        ctx.save_for_backward(logits)  # an output: autograd stores it without a cycle
+        return step.scalars[0].clone(), step.scalars[1].clone(), logits, token
 
     @staticmethod
     def backward(ctx, g_hf, g_kl, g_logits, g_token):
@@ -678,9 +709,10 @@ class _MMTGFunction(torch.autograd.Function):
         dense = g_logits
         if g_hf is not None:
             # HF loss gradient (train.py discards this loss; supported for completeness)
-            hf_dense = torch.empty_like(step.logits)
+            (logits,) = ctx.saved_tensors
+            hf_dense = torch.empty_like(logits)
             g = g_hf.detach().float().contiguous()
-            _lib.check(lib.mmtg_ce_bwd(C.c_void_p(step.logits.data_ptr()), C.c_int64(d.V), C.c_void_p(step.lse_ptr),
+            _lib.check(lib.mmtg_ce_bwd(C.c_void_p(logits.data_ptr()), C.c_int64(d.V), C.c_void_p(step.lse_ptr),
                                        C.c_void_p(step.topic_ids.data_ptr()), C.c_void_p(step.targets.data_ptr()),
                                        None, None, C.c_void_p(g.data_ptr()), C.c_void_p(hf_dense.data_ptr()), 0,
                                        C.c_int64(d.V), d.B, d.L, d.P, d.T, d.V, st), "mmtg_ce_bwd")

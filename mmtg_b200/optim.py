@@ -57,11 +57,45 @@ class FusedAdamW(torch.optim.Optimizer):
         _lib.check(lib.mmtg_adamw_step(C.c_void_p(P.data_ptr()), C.c_void_p(G.data_ptr()),
                                        C.c_void_p(self._m.data_ptr()), C.c_void_p(self._v.data_ptr()),
                                        C.c_void_p(W16.data_ptr()), C.c_int64(P.numel()), C.c_float(g["lr"]),
-                                       C.c_float(g["betas"][0]), C.c_float(g["betas"][1]), C.c_float(g["eps"]),
+                                       C.c_double(g["betas"][0]), C.c_double(g["betas"][1]), C.c_float(g["eps"]),
                                        C.c_float(g["weight_decay"]), self._t, int(g["correct_bias"]), normsq,
                                        C.c_float(self.max_grad_norm or 0.0), C.c_void_p(self._lr_dev.data_ptr()),
                                        C.c_void_p(self._step_dev.data_ptr()), st), "mmtg_adamw_step")
+        self.model.mark_bf16_shadow_fresh()  # the kernel rewrote the bf16 weight shadow itself
         return None
+
+    def sync_lr(self):
+        """Push `param_groups[0]['lr']` (as an LR scheduler leaves it) to the device copy the
+        captured AdamW kernel reads. GraphedTrainStep calls this before every replay."""
+        lr = self.param_groups[0]["lr"]
+        if self._lr_host != lr and self._m is not None:
+            self._lr_dev.fill_(lr)
+            self._lr_host = lr
+
+    def state_dict(self):
+        """torch.optim.Optimizer.state_dict() plus the flat moments and the device step counter
+        (they live outside `self.state`), so save/resume keeps exp_avg, exp_avg_sq and the bias
+        correction."""
+        sd = super().state_dict()
+        if self._m is not None:
+            sd["mmtg_flat"] = {"exp_avg": self._m.detach().cpu(), "exp_avg_sq": self._v.detach().cpu(),
+                               "step": int(self._step_dev.item())}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("mmtg_flat", None)
+        super().load_state_dict(state_dict)
+        if flat is not None:
+            if self.model._flat is None:
+                raise _lib.MMTGError("FusedAdamW.load_state_dict: move the model to its CUDA device and run one "
+                                     "forward (or call model._ensure_flat(device)) first")
+            self._buffers()
+            self._m.copy_(flat["exp_avg"])
+            self._v.copy_(flat["exp_avg_sq"])
+            self._step_dev.fill_(int(flat["step"]))
+            self._t = int(flat["step"])
+            self._lr_host = None
 
     def set_lr(self, lr):
         """Update the learning rate (host + device copy); safe between CUDA-graph replays."""

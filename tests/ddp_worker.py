@@ -1,0 +1,121 @@
+"""Worker of tests/test_ddp_gpu.py (one process per GPU, launched by torch.distributed.run).
+
+SURVEY §4 item 5 / §8e: N-rank all-reduced gradients == single-rank gradients on the concatenated
+batch — with equal shards (AVG all-reduce, also through the segmented CUDA-graph path bench.py
+uses) and with ragged shards (curriculum stage-1 filter, src/train.py:178-183: SUM all-reduce of
+gradients scaled by B_local / B_global). Every rank also runs the single-process step on the full
+batch on its own GPU and compares. Prints one JSON line per rank; exit code 1 on mismatch."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _NoOpt:
+    def step(self):
+        pass
+
+    def zero_grad(self):
+        pass
+
+
+def main():
+    from mmtg_b200 import synth
+    from mmtg_b200.configs import data_config, model_cfgs
+    from mmtg_b200.curriculum import stage_row_indices
+    from mmtg_b200.graph import GraphedTrainStep
+    from mmtg_b200.loss import MyLoss
+    from mmtg_b200.model import MMTG
+    from mmtg_b200.parallel import GradSync, ragged_batch_scale
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    n_layer = int(os.environ.get("MMTG_DDP_TEST_LAYERS", "2"))
+    g2 = {"n_layer": n_layer}
+    table = synth.make_token_table()
+    sd = synth.make_state_dict(0, gpt2_cfg=g2)
+
+    def build():
+        m = MMTG(model_cfgs, data_config(), 13317, train_flag=True, token_table=table, gpt2_config=g2)
+        m.set_dropout(0.0, 0.0, 0.0)
+        m.load_state_dict(sd)
+        return m.to(dev)
+
+    crit = MyLoss(data_config(), model_cfgs)
+    per = 4
+    ratings = np.array(([1, 5, 3, 1, 2, 5, 4, 5] * world)[:per * world])
+    full = synth.batch_to_torch(synth.make_batch(per * world, seed=77, ratings=ratings))
+
+    def take(idx):
+        return {k: v[idx].to(dev) for k, v in full.items()}
+
+    def rel_errors(model, ref):
+        worst, name = 0.0, ""
+        for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            e = (p.grad - q.grad).norm().item() / (q.grad.norm().item() + 1e-6)
+            if q.grad.norm().item() > 1e-4 and e > worst:
+                worst, name = e, n
+        return worst, name
+
+    out = {"rank": rank, "world": world}
+    ok = True
+    # ---------------- single-process references on the concatenated batch ----------------
+    ref3 = build()
+    t_ref3, _, _ = ref3.fused_train_step(take(torch.arange(per * world)), 3, 0.2)
+    idx1 = stage_row_indices(full["rating"], 1)
+    ref1 = build()
+    t_ref1, _, _ = ref1.fused_train_step(take(idx1), 1, 0.2)
+
+    # ---------------- equal shards, AVG all-reduce, eager stage loop ----------------
+    model = build()
+    model.grad_sync = GradSync(average=True)
+    mine = torch.arange(rank * per, (rank + 1) * per)
+    model.fused_train_step(take(mine), 3, 0.2)
+    torch.cuda.synchronize()
+    e, n = rel_errors(model, ref3)
+    out["equal_eager"] = {"worst_rel": e, "param": n}
+    ok &= e <= 3e-3
+    # ---------------- same through the segmented CUDA-graph path (bench.py, N > 1) ----------------
+    step = GraphedTrainStep(model, crit, _NoOpt(), take(mine), alpha=0.2, stage=3, warmup=2)
+    model._flat[2].zero_()
+    step(take(mine))
+    torch.cuda.synchronize()
+    e, n = rel_errors(model, ref3)
+    out["equal_graph"] = {"worst_rel": e, "param": n, "bytes_reduced": model.grad_sync.bytes_reduced}
+    ok &= e <= 3e-3
+    # ---------------- ragged shards: stage-1 filter per rank, SUM all-reduce ----------------
+    model2 = build()
+    model2.grad_sync = GradSync(average=False)
+    local_rows = mine[stage_row_indices(full["rating"][mine], 1)]
+    out["ragged_rows"] = int(len(local_rows))
+    scale = ragged_batch_scale(len(local_rows), device=dev)
+    assert abs(scale - len(local_rows) / len(idx1)) < 1e-9
+    model2.fused_train_step(take(local_rows), 1, 0.2, grad_scale=scale)
+    torch.cuda.synchronize()
+    e, n = rel_errors(model2, ref1)
+    out["ragged"] = {"worst_rel": e, "param": n, "scale": scale}
+    ok &= e <= 3e-3
+    # every rank holds the same reduced gradient bit for bit
+    g = model2._flat[2]
+    chk = torch.stack([g.double().sum(), g.double().abs().sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out["ranks_identical"] = bool(torch.equal(lo, hi))
+    ok &= out["ranks_identical"]
+    out["ok"] = bool(ok)
+    print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
