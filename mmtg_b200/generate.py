@@ -79,6 +79,8 @@ def returned_length(length, sent_len):
 
 # kernels launched through CUDA-graph replays (they bypass the library's launch counter)
 replayed_launches = 0
+# MMTG_GEN_EVENTS=1: device time (ms, CUDA events) of the last call's decode loop (positions after the prefill)
+last_steps_ms = None
 
 
 class _DecodeSession:
@@ -207,6 +209,9 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
         kept.append(logits0[:, -1, :].clone())
     sample(logits0.data_ptr() + 4 * (d.L - 1) * d.V, d.L * d.V)
     remaining = length - 1
+    ev = None
+    if os.environ.get("MMTG_GEN_EVENTS") == "1":
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     graphed = use_cuda_graph and not return_step_logits
     if graphed and ses.graph is None and remaining > 2:
         for _ in range(2):  # eager warm-up (kernel attributes, descriptor cache), then capture
@@ -222,8 +227,10 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
                 one_step()
         torch.cuda.current_stream().wait_stream(side)
         ses.graph = graph
+    global replayed_launches, last_steps_ms
+    if ev:
+        ev[0].record()
     if graphed and ses.graph is not None:
-        global replayed_launches
         for _ in range(remaining):
             ses.graph.replay()
         replayed_launches += remaining * getattr(ses, "launches_per_step", 0)
@@ -232,6 +239,10 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
             one_step()
             if return_step_logits:
                 kept.append(step_logits.clone())
+    if ev:
+        ev[1].record()
+        ev[1].synchronize()
+        last_steps_ms = ev[0].elapsed_time(ev[1]) * (length - 1) / max(1, remaining)
     tm.mark("steps")
     out = gen.cpu().numpy()
     tm.mark("d2h")

@@ -30,9 +30,10 @@ def segment_bounds(nstage: int, group: int):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, example_batch, alpha=0.2, stage=3, warmup=3):
+    def __init__(self, model, criterion, optimizer, example_batch, alpha=0.2, stage=3, warmup=3, grad_scale=1.0):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.alpha, self.stage = alpha, stage
+        self.grad_scale = grad_scale  # B_local / B_global of a ragged data-parallel step (parallel.py)
         self.static = {k: v.detach().clone() for k, v in example_batch.items()}
         self.sync = model.grad_sync
         # capture on a HIGH-priority stream: the engine's weight-gradient side stream has the lowest
@@ -54,7 +55,7 @@ class GraphedTrainStep:
         # segmented capture: collectives are issued eagerly between the segments
         self.g_fwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fwd, stream=self.cap_stream):
-            self.step, self.total, _, _ = model.fused_forward_loss(self.static, stage, alpha)
+            self.step, self.total, _, _ = model.fused_forward_loss(self.static, stage, alpha, grad_scale)
         pool = self.g_fwd.pool()
         self.nstage = self.step.dims.NL + 3
         # backward stages per captured segment: 1 = an all-reduce can start after every block;
@@ -74,7 +75,7 @@ class GraphedTrainStep:
             optimizer.zero_grad()
 
     def _eager(self):
-        total, _loss, _kl = self.model.fused_train_step(self.static, self.stage, self.alpha)
+        total, _loss, _kl = self.model.fused_train_step(self.static, self.stage, self.alpha, self.grad_scale)
         self.optimizer.step()
         self.optimizer.zero_grad()
         return total

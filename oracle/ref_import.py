@@ -1,8 +1,10 @@
-"""ORACLE tooling — imports the UNMODIFIED reference (/root/reference/src) in the build container.
+"""ORACLE tooling — imports the UNMODIFIED reference: /root/reference/src in the build container,
+else the byte-for-byte staged copy oracle/_ref/src (oracle/build_ref.py; git-ignored, travels to
+the GPU box with the snapshot).
 
-/root/reference does not exist on the GPU box, so nothing under tests -m gpu, smoke() or
-bench.py may call this; it is used by scripts/make_golden.py (to write tests/golden/) and by
-tests/test_oracle_vs_reference.py (skipped when the reference tree is absent).
+Used by scripts/make_golden.py (to write tests/golden/), tests/test_oracle_vs_reference.py
+(skipped when neither tree is present) and bench.py's reference arm / cpu_baseline leg
+(`kind: "reference"`): checker and baseline only, never on the product path.
 
 Recipe: a scratch working directory holding config/model_config.json and a
 synthetic vocab/token_id2emb_dict.pkl (the constructor hard-codes both relative paths,
@@ -18,7 +20,8 @@ import shutil
 import sys
 import tempfile
 
-REF_SRC = "/root/reference/src"
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")
+REF_SRC = "/root/reference/src" if os.path.isfile("/root/reference/src/model.py") else _STAGED
 
 
 def available() -> bool:
