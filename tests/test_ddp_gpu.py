@@ -21,9 +21,9 @@ def test_allreduced_gradients_equal_single_rank_gradients(cuda, world):
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "ddp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
-    assert len(lines) == world and all(l["ok"] for l in lines), lines
     out = os.path.join(ROOT, "gpurun_out")
-    if os.path.isdir(out):
-        with open(os.path.join(out, f"ddp_grad_check_n{world}.json"), "w") as f:
-            json.dump(lines, f, indent=1)
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"ddp_grad_check_n{world}.json"), "w") as f:
+        json.dump(lines, f, indent=1)
+    assert r.returncode == 0, (lines, r.stderr[-1500:])
+    assert len(lines) == world and all(l["ok"] for l in lines), lines
