@@ -281,14 +281,25 @@ int mmtg_decode_step(const mmtg_model* m, int32_t Lmax, void* decode_workspace, 
                      float* logits, void* stream);
 /* Fused form of mmtg_decode_step for B <= 64, E = 768: ONE persistent kernel runs every decoder
  * block + ln_f + lm_head of the position (grid-wide barriers between phases, weights and cached
- * K/V prefetched one phase ahead, LayerNorm folded into the following linear layer). Same
- * arguments and results as mmtg_decode_step up to fp32 summation order (split-K partials are
- * combined with atomic adds). Requires mmtg_decode_fold_weights on this workspace after every
- * change of the weights. */
+ * K/V prefetched ahead, LayerNorm folded into the following linear layer). Same arguments and
+ * results as mmtg_decode_step up to rounding (the folded LayerNorm changes the operation order).
+ * Split-K partials are reduced in a FIXED order through distributed shared memory of 4-CTA
+ * clusters: bit-reproducible run to run. Requires mmtg_decode_fold_weights on this workspace
+ * after mmtg_decode_load_prefix and after every change of the weights. */
 int mmtg_decode_fold_weights(const mmtg_model* m, int32_t Lmax, void* decode_workspace, void* stream);
 int mmtg_decode_step_fused(const mmtg_model* m, int32_t Lmax, void* decode_workspace, const int32_t* gen,
                            int32_t gen_ld, const int32_t* j_ptr, int32_t sent_len, int32_t n_sent,
                            float* logits, void* stream);
+/* n_steps consecutive positions in ONE launch of the persistent kernel, each = embedding build +
+ * projector (src/model.py:296-318; layer 1 via the per-call tables table W1^T / ctx W1^T that
+ * mmtg_decode_fold_weights prepares) + all blocks + lm_head + the sampler of mmtg_sample_rows
+ * (same arguments, same RNG stream). On entry gen[:, *j_ptr] must hold the tokens to consume; on
+ * return gen[:, *j_ptr + 1 .. *j_ptr + n_steps] are decided, *j_ptr is advanced by n_steps and
+ * `logits` holds the last position's [B, V] logits. Deterministic: no atomics on the path. */
+int mmtg_decode_steps_fused(const mmtg_model* m, int32_t Lmax, void* decode_workspace, int32_t* gen, int32_t gen_ld,
+                            int32_t* j_ptr, int32_t sent_len, int32_t n_sent, int32_t n_steps, float temperature,
+                            int32_t top_k, float top_p, float rep_penalty, const uint64_t* seed_dev, float* logits,
+                            void* stream);
 /* Debug: per-phase globaltimer stamps of the fused step (CTA 0) into dev_buf (>= 80 x u64). */
 int mmtg_decode_set_trace(uint64_t* dev_buf);
 /* ban_specials: set ids 1, 2, 100, 102 to -inf (src/generate.py:133-136).

@@ -15,6 +15,7 @@
 
 #include "../../include/mmtg_b200.h"
 #include "ops.h"
+#include "sampler.cuh"
 
 namespace mmtg {
 
@@ -68,15 +69,22 @@ void carve_decode(const mmtg_dims& d, int Lmax, uint8_t* base, DWs* w) {
   w->h2 = (float*)take(B * E * 4);
   MegaBufs& g = w->mega;
   g.h = w->h; g.h2 = w->h2; g.att16 = w->att16; g.kcache = w->kcache; g.vcache = w->vcache; g.keymask = w->keymask;
-  g.h_alt = (float*)take(B * E * 4);
-  g.qkv_acc = (float*)take(B * 3 * E * 4);
-  g.u_acc = (float*)take(B * 4 * E * 4);
-  g.row_stats = (float*)take(2 * 64 * 2 * 4);
+  g.h16 = (bf16*)take(64 * E * 2);
+  g.h2_16 = (bf16*)take(64 * E * 2);
+  g.qkv16 = (bf16*)take(64 * 3 * E * 2);
+  g.u16 = (bf16*)take(64 * 4 * E * 2);
+  g.stats1 = (float*)take(64 * 32 * 2 * 4);
+  g.stats2 = (float*)take(64 * 32 * 2 * 4);
   g.barrier = (unsigned int*)take(256);
   g.f_attn = (bf16*)take((size_t)d.NL * E * 3 * E * 2);
   g.f_fc = (bf16*)take((size_t)d.NL * E * 4 * E * 2);
   g.f_wte = (bf16*)take((size_t)d.V * E * 2);
   g.f_vec = (float*)take(((size_t)d.NL * 14 * E + 2 * (size_t)d.V) * 4);
+  g.T1 = (float*)take((size_t)d.V * d.He * 4);
+  g.C1 = (float*)take((size_t)d.S * 64 * d.He * 4);
+  g.w2t = (bf16*)take((size_t)d.He * E * 2);
+  g.table16 = (bf16*)take((size_t)d.V * d.Dw * 2);
+  g.ctx16 = (bf16*)take((size_t)d.S * 64 * d.Dw * 2);
   w->bytes = off;
 }
 
@@ -89,7 +97,10 @@ decode_prep_kernel(const int* __restrict__ gen, int gen_ld, const int* __restric
                    int* __restrict__ keymask, int B, int P, int S, int sent_len, int n_sent, int D,
                    int Lmax, unsigned int* __restrict__ barrier, int table_rows) {
   const int b = blockIdx.x;
-  if (b == 0 && threadIdx.x == 0) *barrier = 0u;  // the megakernel's grid barrier starts from zero
+  if (b == 0 && threadIdx.x == 0) {  // the megakernel's grid barrier starts from zero
+    barrier[0] = 0u;
+    barrier[1] = 0u;
+  }
   const int j = *j_ptr;
   const int tok = gen[b * gen_ld + j];
   if ((unsigned)tok >= (unsigned)table_rows) {
@@ -236,130 +247,7 @@ __global__ void kv_scatter_kernel(const bf16* __restrict__ qkv, bf16* __restrict
   reinterpret_cast<uint32_t*>(vc + dst)[l] = reinterpret_cast<const uint32_t*>(src + 2 * E)[l];
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused sampler, one 1024-thread block per row (src/generate.py:118-142 + 64-94).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
-}
-
-struct ArgMax {
-  float v;
-  int i;
-};
-__device__ __forceinline__ ArgMax argmax_merge(ArgMax a, ArgMax b) {
-  // larger value wins; ties -> smaller index (deterministic)
-  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
-  return a;
-}
-__device__ ArgMax block_argmax(const float* s, int V, ArgMax* red) {
-  ArgMax m{-INFINITY, 0x7fffffff};
-  for (int c = threadIdx.x; c < V; c += blockDim.x) m = argmax_merge(m, ArgMax{s[c], c});
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ArgMax t{__shfl_xor_sync(0xffffffffu, m.v, o), __shfl_xor_sync(0xffffffffu, m.i, o)};
-    m = argmax_merge(m, t);
-  }
-  if (lane_id() == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    ArgMax t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : ArgMax{-INFINITY, 0x7fffffff};
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ArgMax u{__shfl_xor_sync(0xffffffffu, t.v, o), __shfl_xor_sync(0xffffffffu, t.i, o)};
-      t = argmax_merge(t, u);
-    }
-    if (threadIdx.x == 0) red[0] = t;
-  }
-  __syncthreads();
-  const ArgMax r = red[0];
-  __syncthreads();
-  return r;
-}
-
-constexpr int MAX_SURV = 1024;  // top-k survivors kept in shared memory (pure top-p has no cap)
-
-// order-preserving float -> uint32 key (larger float <=> larger key; -inf is the smallest real key)
-__device__ __forceinline__ uint32_t float_key(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// block-wide sum, result broadcast to every thread (`red`: >= 32 floats of shared memory)
-__device__ float block_sum(float a, float* red) {
-  a = warp_sum(a);
-  if (lane_id() == 0) red[threadIdx.x >> 5] = a;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    t = warp_sum(t);
-    if (threadIdx.x == 0) red[0] = t;
-  }
-  __syncthreads();
-  const float r = red[0];
-  __syncthreads();
-  return r;
-}
-
-// Multinomial draw over {c : s[c] >= thr} with weights exp(s[c] - mx); u01 in [0, 1). Threads own
-// contiguous chunks, so the prefix order is the vocabulary order (any fixed order is a valid
-// inverse-CDF draw). Returns the picked id to every thread.
-__device__ int block_draw(const float* s, int V, uint32_t thr_key, float mx, float u01, float* red, int* pick_slot) {
-  const int per = (V + blockDim.x - 1) / blockDim.x;
-  const int c0 = threadIdx.x * per, c1 = min(V, c0 + per);
-  float local = 0.f;
-  for (int c = c0; c < c1; ++c)
-    if (float_key(s[c]) >= thr_key && s[c] != -INFINITY) local += __expf(s[c] - mx);
-  // inclusive scan of the per-thread sums: warp scan + scan of the warp totals
-  float incl = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float t = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((int)lane_id() >= o) incl += t;
-  }
-  if (lane_id() == 31) red[threadIdx.x >> 5] = incl;
-  if (threadIdx.x == 0) *pick_slot = -1;
-  __syncthreads();
-  float base = 0.f, total = 0.f;
-  const int nw = blockDim.x >> 5;
-  for (int w = 0; w < nw; ++w) {
-    if (w < (int)(threadIdx.x >> 5)) base += red[w];
-    total += red[w];
-  }
-  const float u = u01 * total;
-  const float lo = base + incl - local, hi = base + incl;
-  if (local > 0.f && u >= lo && u < hi) {
-    float c2 = lo;
-    int pick = -1;
-    for (int c = c0; c < c1; ++c)
-      if (float_key(s[c]) >= thr_key && s[c] != -INFINITY) {
-        c2 += __expf(s[c] - mx);
-        pick = c;
-        if (u < c2) break;
-      }
-    *pick_slot = pick;  // intervals are disjoint: at most one writer
-  }
-  __syncthreads();
-  int r = *pick_slot;
-  if (r < 0) {  // u fell on a rounding gap at the very top: take the last kept id
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int c = V - 1; c >= 0; --c)
-        if (float_key(s[c]) >= thr_key && s[c] != -INFINITY) {
-          *pick_slot = c;
-          break;
-        }
-    }
-    __syncthreads();
-    r = *pick_slot;
-  }
-  __syncthreads();
-  return r;
-}
-
+// Standalone sampler launch: one 1024-thread block per row (sampler.cuh holds the algorithm).
 __global__ void __launch_bounds__(1024)
 sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ gen, int gen_ld,
                    int* __restrict__ j_ptr, int ban_specials, int V, int sent_len, float temperature,
@@ -367,139 +255,10 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, int* __restri
                    const unsigned long long* __restrict__ seed_dev, float* __restrict__ dbg_probs) {
   if (seed_dev) seed = seed_dev[0];  // device-side seed: the launch stays CUDA-graph replayable
   extern __shared__ float s[];  // [V] working logits
-  __shared__ ArgMax red[32];
-  __shared__ float fred[32];
-  __shared__ float sv[MAX_SURV];
-  __shared__ int si[MAX_SURV];
-  __shared__ int s_n;
+  __shared__ SamplerScratch sc;
   const int b = blockIdx.x;
-  const int i = *j_ptr;  // reference loop index: decides token at position i + 1
-  int* g = gen + (long long)b * gen_ld;
-  int next = -1;
-  if (i > 0 && (i + 2) % sent_len == 0) next = 2;        // forced [#EOS#]   (generate.py:118-120)
-  else if (i > 0 && (i + 2) % sent_len == 1) next = 1;   // forced [#START#] (generate.py:121-123)
-  else if (g[i] == 0 && !dbg_probs) next = 0;            // PAD continuation (generate.py:137-138)
-  if (next < 0) {
-    const float* z = logits + (long long)b * ld;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) s[c] = z[c];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      // repetition penalty: plain division, once per OCCURRENCE, ids 0 and 102 exempt
-      if (rep_penalty != 1.0f)
-        for (int t = 0; t <= i; ++t) {
-          const int id = g[t];
-          if (id != 0 && id != 102 && id < V) s[id] = s[id] / rep_penalty;
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < V; c += blockDim.x) s[c] = s[c] / temperature;
-    __syncthreads();
-    if (threadIdx.x == 0 && ban_specials) {
-      s[1] = -INFINITY; s[2] = -INFINITY; s[100] = -INFINITY; s[102] = -INFINITY;
-    }
-    __syncthreads();
-    const uint64_t rbits = splitmix64(seed ^ splitmix64(((uint64_t)b << 32) | (uint32_t)i));
-    const float u01 = (float)(rbits >> 40) * (1.0f / 16777216.0f);
-    const int kk = top_k > 0 ? min(top_k, V) : 0;
-    if (kk == 0) {
-      // ---- no top-k: pure nucleus (top_p > 0) or plain softmax sampling (top_p == 0) ----
-      // generate.py:81-92 keeps, in descending order, every token whose PRECEDING cumulative
-      // probability is <= p (the first always). With F(v) = sum_{z_j > v} softmax(z)_j that set is
-      // {c : F(z_c) <= p} = {c : z_c >= t*}, t* the smallest float with F(t*) <= p: found by
-      // bisection over the order-preserving integer keys (32 block reductions), no sort and no
-      // survivor cap. Exact ties at the threshold are kept or dropped together.
-      const ArgMax m = block_argmax(s, V, red);
-      uint32_t thr = 0u;  // key threshold: keep {c : key(s[c]) >= thr}, -inf excluded
-      float zsum = 0.f;
-      {
-        float a = 0.f;
-        for (int c = threadIdx.x; c < V; c += blockDim.x) a += __expf(s[c] - m.v);
-        zsum = block_sum(a, fred);
-      }
-      if (top_p > 0.f) {
-        uint32_t lo = 0u, hi = float_key(m.v);  // F(key(max)) = 0 <= p: hi always satisfies
-        while (lo < hi) {
-          const uint32_t mid = lo + ((hi - lo) >> 1);
-          float a = 0.f;
-          for (int c = threadIdx.x; c < V; c += blockDim.x)
-            if (float_key(s[c]) > mid) a += __expf(s[c] - m.v);
-          const float F = block_sum(a, fred) / zsum;
-          if (F <= top_p) hi = mid;
-          else lo = mid + 1;
-        }
-        thr = lo;  // smallest key with F <= p
-      }
-      const int pick = block_draw(s, V, thr, m.v, u01, fred, &s_n);
-      if (dbg_probs) {  // test hook: dense probabilities of the filtered distribution
-        float a = 0.f;
-        for (int c = threadIdx.x; c < V; c += blockDim.x)
-          if (float_key(s[c]) >= thr && s[c] != -INFINITY) a += __expf(s[c] - m.v);
-        const float kept = block_sum(a, fred);
-        float* d = dbg_probs + (long long)b * V;
-        for (int c = threadIdx.x; c < V; c += blockDim.x)
-          d[c] = (float_key(s[c]) >= thr && s[c] != -INFINITY) ? __expf(s[c] - m.v) / kept : 0.f;
-      }
-      next = pick;
-    } else {
-      // ---- top-k (<= 1024): descending selection of the survivors, then nucleus over them ----
-      int n = 0;
-      float kth = -INFINITY;
-      while (n < MAX_SURV) {
-        const ArgMax m = block_argmax(s, V, red);
-        if (m.v == -INFINITY) break;
-        if (n >= kk && m.v < kth) break;  // beyond the k-th value (ties at the k-th are kept)
-        if (n == kk - 1) kth = m.v;
-        if (threadIdx.x == 0) {
-          sv[n] = m.v;
-          si[n] = m.i;
-          s[m.i] = -INFINITY;
-        }
-        __syncthreads();
-        ++n;
-      }
-      if (dbg_probs) {
-        float* d = dbg_probs + (long long)b * V;
-        for (int c = threadIdx.x; c < V; c += blockDim.x) d[c] = 0.f;
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) {
-        int keep = n;
-        if (top_p > 0.f) {
-          // nucleus over the top-k survivors (softmax over survivors only: the rest are -inf)
-          float t = 0.f;
-          for (int c = 0; c < n; ++c) t += __expf(sv[c] - sv[0]);
-          float c2 = 0.f;
-          keep = 0;
-          for (int c = 0; c < n; ++c) {
-            if (c > 0 && c2 > top_p) break;
-            c2 += __expf(sv[c] - sv[0]) / t;
-            ++keep;
-          }
-        }
-        // multinomial over the kept survivors
-        float t = 0.f;
-        for (int c = 0; c < keep; ++c) t += __expf(sv[c] - sv[0]);
-        const float u = u01 * t;
-        float c2 = 0.f;
-        int pick = keep > 0 ? si[keep - 1] : 0;
-        for (int c = 0; c < keep; ++c) {
-          c2 += __expf(sv[c] - sv[0]);
-          if (u < c2) {
-            pick = si[c];
-            break;
-          }
-        }
-        s_n = pick;
-        if (dbg_probs) {
-          float* d = dbg_probs + (long long)b * V;
-          for (int c = 0; c < keep; ++c) d[si[c]] = __expf(sv[c] - sv[0]) / t;
-        }
-      }
-      __syncthreads();
-      next = s_n;
-    }
-  }
-  if (threadIdx.x == 0) g[i + 1] = next;
+  sample_row(logits + (long long)b * ld, gen + (long long)b * gen_ld, b, *j_ptr, ban_specials, V, sent_len, temperature,
+             top_k, top_p, rep_penalty, seed, dbg_probs ? dbg_probs + (long long)b * V : nullptr, s, &sc);
   // the shared step index is advanced by a separate 1-thread kernel (advance_kernel): doing it
   // here would need a grid-wide barrier
 }
@@ -537,9 +296,9 @@ int decode_load_prefix(const mmtg_dims& d, const bf16* const* qkv_layers, const 
   DWs w;
   carve_decode(d, Lmax, (uint8_t*)decode_ws, &w);
   const size_t layer_cache = (size_t)d.B * d.NH * Lmax * 64;
-  // fused step: the qkv accumulator starts from zero (each position leaves it zeroed again); cache
-  // rows past the current position are read as whole 64-key boxes and must hold finite values
-  MMTG_CUDA_OK(cudaMemsetAsync(w.mega.qkv_acc, 0, (size_t)d.B * 3 * d.E * 4, st));
+  // fused step: cache rows past the current position are read as whole 64-key boxes and must hold
+  // finite values; its grid-barrier counter starts from zero
+  MMTG_CUDA_OK(cudaMemsetAsync(w.mega.barrier, 0, 256, st));
   MMTG_CUDA_OK(cudaMemsetAsync(w.kcache, 0, (size_t)d.NL * layer_cache * 2, st));
   MMTG_CUDA_OK(cudaMemsetAsync(w.vcache, 0, (size_t)d.NL * layer_cache * 2, st));
   for (int l = 0; l < d.NL; ++l) {
@@ -593,7 +352,7 @@ int decode_step_impl(const mmtg_model* m, int32_t Lmax, void* decode_ws, const i
     a.rowtab1 = P + o.wte; a.ldt1 = E; a.rowidx1 = w.types;
     MMTG_TRY(decode_gemm(&a, stream));
   }
-  if (fused) return decode_mega_launch(m, Lmax, w.mega, j_ptr, logits, st);
+  if (fused) return decode_mega_launch(m, Lmax, w.mega, const_cast<int*>(j_ptr), logits, nullptr, st);
   const size_t layer_cache = (size_t)B * d.NH * Lmax * 64;
   const int att_smem = (Lmax + 4 + 4 * 64) * 4;
   for (int l = 0; l < d.NL; ++l) {
@@ -641,11 +400,71 @@ extern "C" int mmtg_decode_step_fused(const mmtg_model* m, int32_t Lmax, void* d
   return decode_step_impl(m, Lmax, decode_ws, gen, gen_ld, j_ptr, sent_len, n_sent, logits, stream, true);
 }
 
+namespace mmtg {
+namespace {
+// out[k][n] = bf16(in[n][k])  (nn.Linear [N, K] fp32 -> [K, N] bf16), 32x32 tiles through smem
+__global__ void transpose_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int N, int K) {
+  __shared__ float t[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    t[i][threadIdx.x] = (n < N && k < K) ? in[(long long)n * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    if (k < K && n < N) out[(long long)k * N + n] = __float2bfloat16(t[threadIdx.x][i]);
+  }
+}
+// Full-step mode tables (once per generation call, after mmtg_decode_load_prefix): projector
+// layer 1 (src/model.py:316) is linear in table[tok] + ctx, so table W1^T and ctx W1^T are
+// computed once with the tcgen05 GEMM and each position gathers two rows instead of streaming W1.
+int fold_projector(const mmtg_model* m, const DWs& w, void* stream) {
+  const mmtg_dims& d = m->dims;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* P = m->params;
+  const bf16* W = (const bf16*)m->params_bf16;
+  const int rows = m->table_rows < d.V ? m->table_rows : d.V;
+  transpose_bf16_kernel<<<dim3(cdiv(d.E, 32), cdiv(d.He, 32)), dim3(32, 8), 0, st>>>(P + m->off.proj2_w, w.mega.w2t, d.E, d.He);
+  MMTG_LAUNCH_OK();
+  count_launch();
+  MMTG_TRY(cast_bf16(m->token_table, w.mega.table16, (long long)rows * d.Dw, st));
+  MMTG_TRY(cast_bf16(w.ctx, w.mega.ctx16, (long long)d.S * d.B * d.Dw, st));
+  mmtg_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = w.mega.table16; a.lda = d.Dw; a.B = W + m->off.proj1_w; a.ldb = d.Dw;
+  a.M = rows; a.N = d.He; a.K = d.Dw; a.block_n = 128;
+  a.out = w.mega.T1; a.ldo = d.He; a.out_dtype = MMTG_F32;
+  MMTG_TRY(mmtg_gemm_bf16(&a, stream));
+  a.A = w.mega.ctx16; a.M = d.S * d.B; a.out = w.mega.C1;
+  MMTG_TRY(decode_gemm(&a, stream));
+  return 0;
+}
+}  // namespace
+}  // namespace mmtg
+
 extern "C" int mmtg_decode_fold_weights(const mmtg_model* m, int32_t Lmax, void* decode_ws, void* stream) {
   MMTG_CHECK_ARG(m && decode_ws && m->params, "null argument");
   DWs w;
   carve_decode(m->dims, Lmax, (uint8_t*)decode_ws, &w);
-  return decode_fold_weights(m, w.mega, (cudaStream_t)stream);
+  MMTG_TRY(decode_fold_weights(m, w.mega, (cudaStream_t)stream));
+  return fold_projector(m, w, stream);
+}
+
+extern "C" int mmtg_decode_steps_fused(const mmtg_model* m, int32_t Lmax, void* decode_ws, int32_t* gen, int32_t gen_ld,
+                                       int32_t* j_ptr, int32_t sent_len, int32_t n_sent, int32_t n_steps,
+                                       float temperature, int32_t top_k, float top_p, float rep_penalty,
+                                       const uint64_t* seed_dev, float* logits, void* stream) {
+  MMTG_CHECK_ARG(m && decode_ws && gen && j_ptr && logits && n_steps >= 1, "bad decode_steps_fused arguments");
+  MMTG_CHECK_ARG(m->dims.B <= 64 && m->dims.E == 768 && m->dims.NH * 64 == m->dims.E && Lmax <= 1024,
+                 "fused decode steps support B <= 64, E = 768, head dim 64, Lmax <= 1024");
+  DWs w;
+  carve_decode(m->dims, Lmax, (uint8_t*)decode_ws, &w);
+  MegaStepArgs fa;
+  fa.n_steps = n_steps; fa.gen = gen; fa.gen_ld = gen_ld; fa.sent_len = sent_len; fa.n_sent = n_sent;
+  fa.temperature = temperature; fa.top_k = top_k; fa.top_p = top_p; fa.rep_penalty = rep_penalty;
+  fa.seed_dev = (const unsigned long long*)seed_dev;
+  return decode_mega_launch(m, Lmax, w.mega, j_ptr, logits, &fa, (cudaStream_t)stream);
 }
 
 extern "C" int mmtg_sample_rows(const float* logits, int64_t ld, int32_t* gen, int32_t gen_ld,

@@ -61,18 +61,30 @@ int beta_bwd(const float* topic, const float* img, const float* txt, const float
 
 // decode_mega.cu: buffers of the fused decode step (carved from the decode workspace)
 struct MegaBufs {
-  float *h, *h_alt, *h2, *qkv_acc, *u_acc;
-  float* row_stats;  // [2][64][2]: (mean, rstd) of h rows, then of h2 rows
-  bf16* att16;
+  float *h, *h2;                            // fp32 residual stream [64][E]: block input / after attention
+  bf16 *h16, *h2_16, *qkv16, *att16, *u16;  // bf16 GEMM operands: [64][E], [64][E], [64][3E], [64][E], [64][4E]
+  float *stats1, *stats2;                   // [64][32][2] per-row (sum, sumsq) partials per column chunk (LN1/ln_f, LN2)
   bf16 *kcache, *vcache;
-  const int* keymask;
-  unsigned int* barrier;
+  int* keymask;
+  unsigned int* barrier;  // [0] grid-barrier counter (runs on across launches), [1] its value at launch start
+  // full-step mode: projector layer 1 folded into two tables (layer 1 is linear in table[tok] + ctx)
+  float *T1, *C1;             // table W1^T [V][He], ctx W1^T [S*B][He]  (fp32, bias b1 NOT included)
+  bf16 *w2t, *table16, *ctx16;  // projector layer 2 transposed [He][E]; bf16 staging of the GEMM operands
   // LayerNorm-folded weights (mmtg_decode_fold_weights)
   bf16 *f_attn, *f_fc, *f_wte;  // [NL][E][3E], [NL][E][4E], [V][E]
   float* f_vec;                 // per layer: cs_attn[3E] b_attn[3E] cs_fc[4E] b_fc[4E]; then cs_head[V] b_head[V]
 };
-int decode_mega_launch(const mmtg_model* m, int Lmax, const MegaBufs& bufs, const int* j_ptr, float* logits,
-                       cudaStream_t st);
+struct MegaStepArgs {  // full-step mode (embedding + projector prologue and sampler inside the kernel)
+  int n_steps;
+  int* gen;
+  int gen_ld, sent_len, n_sent;
+  float temperature;
+  int top_k;
+  float top_p, rep_penalty;
+  const unsigned long long* seed_dev;
+};
+int decode_mega_launch(const mmtg_model* m, int Lmax, const MegaBufs& bufs, int* j_ptr, float* logits,
+                       const MegaStepArgs* full, cudaStream_t st);
 int decode_fold_weights(const mmtg_model* m, const MegaBufs& bufs, cudaStream_t st);
 
 }  // namespace mmtg

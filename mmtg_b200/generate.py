@@ -4,9 +4,10 @@
 repitition_penalty, device)` keeps the reference's signature (sic: `repitition`) and return value
 (the token list WITHOUT the last appended token). Underneath, the reference's "re-run the whole
 model on the whole prefix per token" loop is replaced by a KV-cached decode engine:
-one training-style forward over [prompt | first token], then one fused step per position
-(mmtg_decode_step + mmtg_sample_rows, both hand-written CUDA; the step index lives on the
-device so the step is replayed from a CUDA graph). `sample_sequence_batch` runs B independent
+one training-style forward over [prompt | first token], then ONE persistent-kernel launch that
+decodes every remaining position (mmtg_decode_steps_fused: embedding, projector, 12 blocks, lm_head
+and the sampler per position, grid barriers in between; B <= 64), or per-op launches replayed from
+a CUDA graph (mmtg_decode_step + mmtg_sample_rows; B > 64). `sample_sequence_batch` runs B independent
 batch-1 reference runs at once (BASELINE.json configs[3]: batch 64).
 """
 from __future__ import annotations
@@ -157,13 +158,12 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
     step = logits0._mmtg_step
     d = step.dims
     sampling = (float(temperature), int(top_k), float(top_p), float(repitition_penalty))
-    # Fused persistent-kernel step for B <= 64 (~2x the per-op path). Its split-K partials are
-    # combined with atomic adds, so logits move by a few 1e-3 between runs (summation order ->
-    # bf16 rounding of downstream operands): greedy ids are reproducible except at top-2 margins
-    # of that size (measured: the only run-to-run differences in tests/test_generate_gpu.py sit at
-    # the two smallest margins of the test rows, 0.0027 and 0.0038). MMTG_DECODE_MEGA=0 selects
-    # the per-op launches, which are bit-reproducible.
-    fused = Bn <= 64 and d.E == 768 and d.P + length + 1 <= 1024 and os.environ.get("MMTG_DECODE_MEGA", "1") != "0"
+    # Persistent decode kernel for B <= 64: embedding + projector + all blocks + lm_head + sampler of
+    # EVERY remaining position in ONE launch (mmtg_decode_steps_fused). Split-K partials are reduced
+    # in a fixed order through cluster shared memory: bit-reproducible. MMTG_DECODE_MEGA=0 selects
+    # the per-op launches (~90 kernels per position, the only path for B > 64).
+    fused = (Bn <= 64 and d.E == 768 and d.P + length + 1 <= 1024 and d.He == 512 and 0 <= int(top_k) <= 1024
+             and os.environ.get("MMTG_DECODE_MEGA", "1") != "0")
     key = (Bn, length, str(dev), sampling, model._flat[0].data_ptr(), model._table(dev).data_ptr(), fused)
     sessions = model.__dict__.setdefault("_decode_sessions", {})
     ses = sessions.get(key)
@@ -191,15 +191,32 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
                                         C.c_uint64(0), C.c_void_p(ses.seed.data_ptr()), 1, None,
                                         C.c_void_p(_lib.stream_ptr())), "mmtg_sample_rows")
 
-    step_fn = lib.mmtg_decode_step_fused if fused else lib.mmtg_decode_step
-    if fused:  # LayerNorm-folded weight copies follow the current parameters
+    if fused:  # LayerNorm-folded weight copies and the projector tables follow the current parameters / context
         _lib.check(lib.mmtg_decode_fold_weights(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), st),
                    "mmtg_decode_fold_weights")
 
+    def fused_steps(n):
+        """n positions in one launch: consumes gen[:, j], decides gen[:, j+1 .. j+n], advances j by n."""
+        _lib.check(lib.mmtg_decode_steps_fused(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), C.c_void_p(gen.data_ptr()),
+                                               gen_ld, C.c_void_p(j.data_ptr()), sent_len, n_sent, int(n),
+                                               C.c_float(temperature), int(top_k), C.c_float(top_p),
+                                               C.c_float(repitition_penalty), C.c_void_p(ses.seed.data_ptr()),
+                                               C.c_void_p(step_logits.data_ptr()), C.c_void_p(_lib.stream_ptr())),
+                   "mmtg_decode_steps_fused")
+
+    # MMTG_DECODE_MEGA=2: the step-only entry of the persistent kernel (mmtg_decode_step_fused: blocks +
+    # lm_head in the kernel; embedding / projector / sampler as separate launches) — kept for callers
+    # that drive their own sampler, and cross-checked against the full-step mode in the tests
+    step_only = fused and os.environ.get("MMTG_DECODE_MEGA", "1") == "2"
+    step_fn = lib.mmtg_decode_step_fused if step_only else lib.mmtg_decode_step
+
     def one_step():
+        if fused and not step_only:
+            fused_steps(1)
+            return
         _lib.check(step_fn(C.byref(cm), Lmax, C.c_void_p(dws.data_ptr()), C.c_void_p(gen.data_ptr()),
-                           gen_ld, C.c_void_p(j.data_ptr()), sent_len, n_sent,
-                           C.c_void_p(step_logits.data_ptr()), C.c_void_p(_lib.stream_ptr())),
+                                        gen_ld, C.c_void_p(j.data_ptr()), sent_len, n_sent,
+                                        C.c_void_p(step_logits.data_ptr()), C.c_void_p(_lib.stream_ptr())),
                    "mmtg_decode_step")
         sample(step_logits.data_ptr(), d.V)
 
@@ -212,7 +229,7 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
     ev = None
     if os.environ.get("MMTG_GEN_EVENTS") == "1":
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    graphed = use_cuda_graph and not return_step_logits
+    graphed = use_cuda_graph and not return_step_logits and (not fused or step_only)
     if graphed and ses.graph is None and remaining > 2:
         for _ in range(2):  # eager warm-up (kernel attributes, descriptor cache), then capture
             l0 = _lib.launch_count()
@@ -230,7 +247,16 @@ def sample_sequence_batch(model, start_inputs, length, tokenizer=None, temperatu
     global replayed_launches, last_steps_ms
     if ev:
         ev[0].record()
-    if graphed and ses.graph is not None:
+    if fused and not step_only and not return_step_logits and remaining > 0:
+        # use_cuda_graph=False: one launch per position (same kernel, n_steps = 1) instead of one per call
+        l0 = _lib.launch_count()
+        if use_cuda_graph:
+            fused_steps(remaining)
+        else:
+            for _ in range(remaining):
+                fused_steps(1)
+        ses.launches_per_step = (_lib.launch_count() - l0) / remaining
+    elif graphed and ses.graph is not None:
         for _ in range(remaining):
             ses.graph.replay()
         replayed_launches += remaining * getattr(ses, "launches_per_step", 0)

@@ -28,24 +28,18 @@ sample_sequence_batch(model, starts, 220, device="cuda", use_cuda_graph=False, t
                       repitition_penalty=1.0)
 torch.cuda.synchronize()
 t = buf.cpu().numpy()
-n = 62
+# stamps: kernel start, after the prologue barrier, after each of the 5 phase barriers of the 12 blocks, kernel end
+n = 2 + 5 * 12 + 1
 d = np.diff(t[:n]) / 1e3
-print("total us", d.sum())
+print("total us %.1f  prologue %.2f" % (d.sum(), d[0]))
 for ph in "ABCDE":
-    v = [d[5 * l + "ABCDE".index(ph)] for l in range(12)]
+    v = [d[1 + 5 * l + "ABCDE".index(ph)] for l in range(12)]
     print(ph, "mean %.2f us  min %.2f max %.2f" % (np.mean(v), np.min(v), np.max(v)))
-print("F %.2f" % d[60])
-a0 = t[5 * 11]  # stamp at the start of the last block's phase A
-sub = t[64:70]
-print("phase A (last block) sub-stamps us from phase start [stats, side+sync, stage, wait+sync, mma+red, prefetch]:",
-      [round(float(x - a0) / 1e3, 2) for x in sub], "end", round(float(t[5 * 11 + 1] - a0) / 1e3, 2))
-arrA = (t[80:80 + 148] - a0) / 1e3
-arrB = (t[240:240 + 148] - t[5 * 11 + 1]) / 1e3
-print("arrival at A->B barrier (us after CTA0 phase start): min %.2f med %.2f max %.2f argmax %d" % (arrA.min(), np.median(arrA), arrA.max(), arrA.argmax()))
-print("  sorted tail:", np.sort(arrA)[-8:].round(2), "ctas", np.argsort(arrA)[-8:])
-print("arrival at B->C barrier (us after CTA0 B start): min %.2f med %.2f max %.2f argmax %d" % (arrB.min(), np.median(arrB), arrB.max(), arrB.argmax()))
-print("  sorted tail:", np.sort(arrB)[-8:].round(2), "ctas", np.argsort(arrB)[-8:])
-f0 = t[60]
-print("phase F sub-stamps us [staged, unit0, unit1, unit2]:", [round(float(x - f0) / 1e3, 2) for x in t[72:76]])
-arr0 = (t[400:400 + 148] - a0) / 1e3
-print("reached A->B arrive: min %.2f med %.2f max %.2f" % (arr0.min(), np.median(arr0), arr0.max()), " tail", np.sort(arr0)[-6:].round(2))
+print("F %.2f" % d[61])
+names = ["start", "acts landed", "weights landed", "mma done", "cluster sync 1", "finalize done", "cluster sync 2", "grid arrive", "window done", "grid wait done"]
+for label, o in (("A", 80), ("C", 90), ("D", 100), ("E", 110)):
+    v = t[o:o + 10].astype(np.float64)
+    base = v[0]
+    print(label, "(last block, CTA 0) us from phase start:", {names[i]: round((v[i] - base) / 1e3, 2) for i in range(10) if v[i] > 0})
+v = t[120:123].astype(np.float64)
+print("B (last block, CTA 0 thread 0): attention work %.2f us, arrive %.2f us" % ((v[1] - v[0]) / 1e3, (v[2] - v[1]) / 1e3))
