@@ -439,6 +439,9 @@ struct EpiGelu {  // u16 = bf16(gelu_new(rstd (acc - mean cs) + b'))
 // 32 + 32 tensor-core instructions per box instead of ~1000 scalar ones. Online softmax across
 // boxes; keys past `pos` and padded keys are masked by selection, never by arithmetic.
 // ---------------------------------------------------------------------------------------------
+// generic-proxy writes (cache rows appended by earlier positions of this launch, shared memory read
+// by ldmatrix) ordered before the async-proxy (TMA) accesses that follow, for every state space
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void attn_issue(const MegaParams& p, int layer, int u, int c, uint8_t* wbuf, uint64_t* bars) {
   const int row = ((layer * p.B * p.NH + u) * p.Lmax) + c * 64;
   uint8_t* buf = wbuf + (c & 1) * 16384;
@@ -466,7 +469,7 @@ __device__ __forceinline__ void attn_warp(const MegaParams& p, int layer, int u,
   const int b = u / NH, h = u - b * NH;
   const int nch = pos / 64 + 1;
   if (!prefetched && l == 0) {
-    fence_proxy_async();
+    fence_proxy_async_all();
     attn_issue(p, layer, u, 0, wbuf, bars);
     if (nch > 1) attn_issue(p, layer, u, 1, wbuf, bars);
   }
@@ -599,7 +602,7 @@ __device__ __forceinline__ void attn_warp(const MegaParams& p, int layer, int u,
     }
     __syncwarp();
     if (c + 2 < nch && l == 0) {
-      fence_proxy_async();
+      fence_proxy_async_all();
       attn_issue(p, layer, u, c + 2, wbuf, bars);
     }
   }
@@ -822,7 +825,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
       if (warp < ATT_WARPS && lane_id() == 0) {
         const int u = cta + G * warp;
         if (u < B * NH) {
-          fence_proxy_async();
+          fence_proxy_async_all();
           attn_issue(p, layer, u, 0, wbuf, wbars);
           if (pos >= 64) attn_issue(p, layer, u, 1, wbuf, wbars);
         }
