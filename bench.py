@@ -485,8 +485,17 @@ def main():
     model.load_state_dict(synth.make_state_dict(0))  # identical replicas on every rank
     model.set_dropout(args.dropout, args.dropout, args.dropout)
     model.to(dev)
+    equal_scale = 1.0
     if world > 1:
-        model.grad_sync = GradSync()
+        # default: AVG all-reduce -> NCCL picks RING / LL128 on 32 channels. MMTG_DDP_SUM=1: SUM all-reduce of
+        # gradients whose loss was pre-scaled by 1 / world -> NCCL picks NVLS / SIMPLE on 24 channels (in-switch
+        # reduction). Measured at 8 GPUs (profiles/r2_nccl_n8_algo.txt): 9.56 ms/step vs 9.65 ms/step — the NVLS
+        # kernels slow the concurrent backward GEMMs a little more (55.3 vs 52.6 us per dominant launch).
+        if os.environ.get("MMTG_DDP_SUM") == "1":
+            model.grad_sync = GradSync(average=False)
+            equal_scale = 1.0 / world
+        else:
+            model.grad_sync = GradSync()
     crit = MyLoss(dcfg, model_cfgs)
     opt = FusedAdamW(model, lr=1e-5, max_grad_norm=1.0)
     stage = args.stage
@@ -498,7 +507,7 @@ def main():
         rr.shuffle(ratings)
     host = synth.batch_to_torch(synth.make_batch(B, seed=1234 + rank, data_config=dcfg, ratings=ratings))
     b_before = B
-    grad_scale = 1.0
+    grad_scale = equal_scale
     if stage in (1, 2):  # the reference's rating filter (src/train.py:178-183): per-rank row counts differ
         from mmtg_b200.curriculum import stage_row_indices
         from mmtg_b200.parallel import ragged_batch_scale
