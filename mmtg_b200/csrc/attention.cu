@@ -495,7 +495,7 @@ int attn_fwd_impl(const bf16* qkv, const int* kmask, bf16* out, float* lse, int 
   return 0;
 }
 
-int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float* lse, const float* delta,
+int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
                 bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop);
 
 int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
@@ -518,13 +518,11 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
   p.dqkv = dqkv; p.B = B; p.L = L; p.NH = NH; p.E = NH * HD; p.scale = 0.125f;
   if (drop_on(drop)) { p.drop_seed = drop->seed; p.drop_site = drop->site; p.drop_p = drop->p; }
   ProfScope prof(1, 2.5 * 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 8 * B * L * NH * 64, st);
+  // (the whole-head tcgen05 kernel forms delta = rowsum(dO * O) in its own prologue)
+  if (use_tc && L <= 256) return attn_bwd_tc(qkv, kmask, out, dout, lse, dqkv, B, L, NH, st, drop);
   const long long warps = (long long)B * L;
   attn_delta_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, st>>>(out, dout, delta, B, L, NH, p.E);
   MMTG_LAUNCH_OK();
-  if (use_tc && L <= 256) {
-    count_launch();
-    return attn_bwd_tc(qkv, kmask, dout, lse, delta, dqkv, B, L, NH, st, drop);
-  }
   dim3 grid(cdiv(L, BQ), B * NH);
   constexpr int BWD_SMEM = 6 * BQ * HD * 2 + 4 * BQ * 4;  // 6 bf16 tiles + 4 x 64 floats
   MMTG_PER_DEVICE_FLAG(attr_set);

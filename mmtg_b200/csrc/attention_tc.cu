@@ -41,17 +41,37 @@ struct AttnTcParams {
 };
 
 constexpr int SMEM_Q = 0, SMEM_K = 16384, SMEM_V = 32768, SMEM_P = 49152, SMEM_BAR = 81920;
-constexpr int SMEM_TOTAL = SMEM_BAR + 64 + 4096 + 1024;  // + barriers, key mask (<= 1024 keys), slack
+// after the barriers: key-mask bits (<= 1024 keys), the row-max exchange (double-buffered by key
+// block parity) and the row-sum exchange of the two threads that share a query row
+constexpr int SMEM_KBITS = SMEM_BAR + 64, SMEM_RED = SMEM_BAR + 256, SMEM_SUM = SMEM_RED + 2048;
+constexpr int SMEM_TOTAL = SMEM_BAR + 64 + 4096 + 1024;
+constexpr int FW_SM_WARPS = 8;                     // softmax warps: 2 per TMEM lane quadrant, 64 keys of a block each
+constexpr int FW_THREADS = FW_SM_WARPS * 32 + 32;  // + the control warp
 
 #define ATT_TRACE(code)                                                                  \
   do {                                                                                   \
     if (p.trace && lane == 0) {                                                          \
-      p.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + warp] = (code);                \
+      p.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + warp] = (code);               \
       __threadfence_system();                                                            \
     }                                                                                    \
   } while (0)
 
-__global__ void __launch_bounds__(160)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// the two warps of a TMEM lane quadrant (64 threads) meet on named barrier 1 + quadrant
+__device__ __forceinline__ void quad_sync(int qd) {  // immediate ids: only barriers 0-4 are reserved
+  switch (qd) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+__global__ void __launch_bounds__(FW_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -61,7 +81,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
   uint64_t* bar_p = bar_q + 3;
   uint64_t* bar_o = bar_q + 4;
   uint32_t* tmem_slot = (uint32_t*)(bar_q + 5);
-  float* s_mask = (float*)(smem + SMEM_BAR + 64);  // [<= 1024] additive key mask of the whole row
+  uint32_t* s_kbits = (uint32_t*)(smem + SMEM_KBITS);  // bit t of word w: key 32 w + t is attendable
+  float* s_red = (float*)(smem + SMEM_RED);            // [2 (block parity)][2 (half)][128 rows]
+  float* s_sum = (float*)(smem + SMEM_SUM);            // [2 (half)][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (gridDim.x - 1) - blockIdx.x;  // heavy tiles first
@@ -75,17 +97,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
     mbar_init(bar_q, 1);
     mbar_init(bar_kv, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, FW_SM_WARPS * 32);
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == FW_SM_WARPS) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
-  for (int k = threadIdx.x; k < nkv * TK; k += blockDim.x) {
+  for (int w0 = warp; w0 < nkv * (TK / 32); w0 += FW_THREADS / 32) {  // warp-uniform: one ballot word each
+    const int k = w0 * 32 + lane;
     const bool ok = k < p.L && (p.kmask == nullptr || p.kmask[b * p.L + k] != 0);
-    s_mask[k] = ok ? 0.f : -INFINITY;
+    const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_kbits[w0] = bits;
   }
   tc_fence_before();
   __syncthreads();
@@ -94,7 +118,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
   ATT_TRACE(1);
 
-  if (warp == 4) {
+  if (warp == FW_SM_WARPS) {
     // ===================== control warp: TMA + MMA =====================
     if (lane == 0) {
       tma_prefetch_desc(&tm);
@@ -136,46 +160,67 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
     __syncwarp();
     ATT_TRACE(90);
   } else {
-    // ===================== softmax warps: one thread per query row =====================
-    const int r = warp * 32 + lane;  // TMEM lane == row within the tile
+    // ===================== softmax warps: TWO threads per query row =====================
+    // warp w owns TMEM lane quadrant w % 4 (rows 32 (w % 4) .. +31) and the key half hf = w / 4 of
+    // every block (32-key chunks 2 hf and 2 hf + 1, and the 32 O columns of that half): the row
+    // maximum and the row sum are exchanged through shared memory between the two warps of a quadrant.
+    const int qd = warp & 3, hf = warp >> 2;
+    const int r = qd * 32 + lane;  // TMEM lane == row within the tile
     const int q = q0 + r;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * LOG2E;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = smem + SMEM_P + r * 128;
+    float m_run = -INFINITY, l_run = 0.f;  // l_run: this thread's half of the row sum
+    uint8_t* prow = smem + SMEM_P + r * 128 + hf * 16384;
     const bool dropping = p.drop_p > 0.f;
     DropKey dk = {0u, 0u, 0u, 1.f};
     if (dropping) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
     // pair index of (this row, key 0): the row sum uses the undropped P, O the dropped one
     const uint32_t pair_row = (uint32_t)((b * p.NH + h) * p.L + q) * (uint32_t)((p.L + 1) >> 1);
     for (int j = 0; j < nkv; ++j) {
-      const float* kmask_j = s_mask + j * TK;  // key padding + sequence end, this block
       ATT_TRACE(20 + 100 * j);
+      // On the diagonal block every key of chunk c > qd lies in the causal future of all 32 rows
+      // of this warp: those chunks are skipped (P = 0 written without reading S).
+      const int cmax = (j == qt) ? qd : TK / 32 - 1;
+      uint32_t vm[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = 2 * hf + t;
+        vm[t] = s_kbits[j * (TK / 32) + c];
+        if (j == qt) {
+          const int lim = r - c * 32;  // key t of the chunk is allowed iff t <= lim
+          vm[t] = lim < 0 ? 0u : (lim < 31 ? (vm[t] & ((2u << lim) - 1u)) : vm[t]);
+        }
+      }
       mbar_wait<15>(bar_s, (uint32_t)(j & 1));
       ATT_TRACE(21 + 100 * j);
       tc_fence_after();
-      // On the diagonal block every key of chunk c > warp lies in the causal future of all 32
-      // rows of this warp: those chunks are skipped (P = 0 written without reading S).
-      const int cmax = (j == qt) ? warp : TK / 32 - 1;
-      // pass 1: row maximum
+      // pass 1: maximum over this thread's 64 keys (scaled to the exp2 domain)
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c <= cmax; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_addr + c * 32, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kc = c * 32 + i;
-          float s = __uint_as_float(v[i]) * sl2 + kmask_j[kc];
-          if (j * TK + kc > q) s = -INFINITY;
-          mx = fmaxf(mx, s);
+      for (int t = 0; t < 2; ++t) {
+        const int c = 2 * hf + t;
+        if (c <= cmax) {  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tS + lane_addr + c * 32, v);
+          tmem_ld_wait();
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmaxf(m0, ((vm[t] >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+            m1 = fmaxf(m1, ((vm[t] >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : -INFINITY);
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
         }
       }
+      mx *= sl2;  // sl2 > 0: max commutes with the scale; -inf stays -inf
+      float* red = s_red + (j & 1) * 256;
+      red[hf * 128 + r] = mx;
+      quad_sync(qd);
+      mx = fmaxf(mx, red[(hf ^ 1) * 128 + r]);
       ATT_TRACE(22 + 100 * j);
       const float m_new = fmaxf(m_run, mx);
       const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-      const float corr = exp2f(m_run - m_safe);  // 0 when m_run = -inf
+      const float corr = ex2_approx(m_run - m_safe);  // 0 when m_run = -inf
       if (j > 0) {
         // O holds the unnormalised sum up to block j-1: rescale it before PV(j) accumulates
         mbar_wait<16>(bar_o, (uint32_t)((j - 1) & 1));
@@ -183,59 +228,56 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
         tc_fence_after();
         // tcgen05.ld/st are .sync.aligned: the whole warp takes the branch together
         if (p.dbg != 1 && __any_sync(0xffffffffu, corr != 1.f)) {
-#pragma unroll 1
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tO + lane_addr + c * 32, v);
-            tmem_ld_wait();
+          uint32_t v[32];
+          tmem_ld_32x32(tO + lane_addr + hf * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
-            if (p.dbg != 2) tmem_st_32x32(tO + lane_addr + c * 32, v);
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+          if (p.dbg != 2) {
+            tmem_st_32x32(tO + lane_addr + hf * 32, v);
+            tmem_st_wait();
           }
-          if (p.dbg != 2) tmem_st_wait();
         }
       }
       ATT_TRACE(24 + 100 * j);
       // pass 2: P = exp2(s - m), row sum, bf16 P into swizzled smem (K-major A operand)
       float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < TK / 32; ++c) {
-        if (c > cmax) {  // warp-uniform
-          uint8_t* half = prow + (c >> 1) * 16384;
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            *reinterpret_cast<uint4*>(half + ((((c & 1) * 4 + t) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+      for (int t = 0; t < 2; ++t) {
+        const int c = 2 * hf + t;
+        if (c > cmax) {  // warp-uniform
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(prow + (((t * 4 + u) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
           continue;
         }
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_addr + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
+        const uint32_t pair0 = pair_row + (uint32_t)((j * TK + c * 32) >> 1);
+        float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const int kc = c * 32 + i;
-          float s0 = __uint_as_float(v[i]) * sl2 + kmask_j[kc];
-          float s1 = __uint_as_float(v[i + 1]) * sl2 + kmask_j[kc + 1];
-          if (j * TK + kc > q) s0 = -INFINITY;
-          if (j * TK + kc + 1 > q) s1 = -INFINITY;
-          float e0 = exp2f(s0 - m_safe), e1 = exp2f(s1 - m_safe);
-          rs += e0 + e1;
+          const float x0 = ((vm[t] >> i) & 1u) ? fmaf(__uint_as_float(v[i]), sl2, -m_safe) : -INFINITY;
+          const float x1 = ((vm[t] >> (i + 1)) & 1u) ? fmaf(__uint_as_float(v[i + 1]), sl2, -m_safe) : -INFINITY;
+          float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+          rs0 += e0;
+          rs1 += e1;
           if (dropping) {  // the 1/(1-p) factor is applied once, at the end
-            const uint32_t bits = drop_bits(dk, pair_row + (uint32_t)((j * TK + kc) >> 1));
+            const uint32_t bits = drop_bits(dk, pair0 + (uint32_t)(i >> 1));
             e0 = drop_keep_lo(dk, bits) ? e0 : 0.f;
             e1 = drop_keep_hi(dk, bits) ? e1 : 0.f;
           }
-          __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+          __nv_bfloat162 tt = __floats2bfloat162_rn(e0, e1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&tt);
         }
-        // 32 keys = 4 x 16-byte chunks; chunk index within the 64-key half: (c & 1) * 4 + t
-        uint8_t* half = prow + (c >> 1) * 16384;
+        rs += rs0 + rs1;
+        // 32 keys = 4 x 16-byte chunks; chunk index within the 64-key half: t * 4 + u
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int cc = (c & 1) * 4 + t;
-          *reinterpret_cast<uint4*>(half + ((cc ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-        }
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(prow + (((t * 4 + u) ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
       }
       l_run = l_run * corr + rs;
       m_run = m_new;
@@ -244,43 +286,43 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
       mbar_arrive(bar_p);
       ATT_TRACE(25 + 100 * j);
     }
-    // finalize
+    // finalize: total row sum = the two halves
+    s_sum[hf * 128 + r] = l_run;
+    quad_sync(qd);
+    const float l_tot = l_run + s_sum[(hf ^ 1) * 128 + r];
     mbar_wait<17>(bar_o, (uint32_t)((nkv - 1) & 1));
     ATT_TRACE(30);
     tc_fence_after();
-    const float inv = (l_run > 0.f ? 1.f / l_run : 0.f) * dk.inv_keep;
+    const float inv = (l_tot > 0.f ? 1.f / l_tot : 0.f) * dk.inv_keep;
     {
       // tcgen05.ld is .sync.aligned: every lane of the warp loads (rows beyond the sequence
       // included); only the global stores are predicated
-      bf16* dst = p.out + ((long long)row0 + q) * p.E + h * HD;
-#pragma unroll 1
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tO + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (q < p.L) {
+      bf16* dst = p.out + ((long long)row0 + q) * p.E + h * HD + hf * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(tO + lane_addr + hf * 32, v);
+      tmem_ld_wait();
+      if (q < p.L) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint32_t w[4];
+        for (int t = 0; t < 4; ++t) {
+          uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * inv,
-                                                       __uint_as_float(v[8 * t + 2 * e + 1]) * inv);
-              w[e] = *reinterpret_cast<uint32_t*>(&x);
-            }
-            *reinterpret_cast<uint4*>(dst + c * 32 + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * inv,
+                                                     __uint_as_float(v[8 * t + 2 * e + 1]) * inv);
+            w[e] = *reinterpret_cast<uint32_t*>(&x);
           }
+          *reinterpret_cast<uint4*>(dst + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        if (hf == 0 && p.lse)
+          p.lse[((long long)b * p.NH + h) * p.L + q] =
+              l_tot > 0.f ? (m_run + log2f(l_tot)) / LOG2E : -INFINITY;
       }
-      if (q < p.L && p.lse)
-        p.lse[((long long)b * p.NH + h) * p.L + q] =
-            l_run > 0.f ? (m_run + log2f(l_run)) / LOG2E : -INFINITY;
     }
   }
   ATT_TRACE(40);
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == FW_SM_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -316,7 +358,7 @@ int attn_fwd_tc(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B,
   p.trace = g_attn_trace;
   ProfScope prof(1, 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 4 * B * L * NH * 64, st);
   dim3 grid(cdiv(L, TQ), B * NH);
-  attn_fwd_tc_kernel<<<grid, 160, SMEM_TOTAL, st>>>(tm, p);
+  attn_fwd_tc_kernel<<<grid, FW_THREADS, SMEM_TOTAL, st>>>(tm, p);
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;
@@ -342,7 +384,8 @@ namespace {
 struct AttnBwdTcParams {
   const int* kmask;     // [B, L]
   const float* lse;     // [B, NH, L]
-  const float* delta;   // [B, NH, L]
+  const bf16* out;      // [B*L, E] forward output O   (delta = rowsum(dO * O) is formed in the prologue)
+  const bf16* dout;     // [B*L, E]
   bf16* dqkv;           // [B*L, 3E]
   int B, L, NH, E;
   float scale;
@@ -351,24 +394,28 @@ struct AttnBwdTcParams {
   float drop_p;
 };
 
-// smem map (bytes): 8 operand tiles of 16 KB, then P and dS (32 KB each), then barriers + masks
+// smem map (bytes): 8 operand tiles of 16 KB, then P and dS (32 KB each), then barriers, key-mask
+// bits and the per-row delta
 constexpr int BW_Q = 0, BW_K = 32768, BW_V = 65536, BW_DO = 98304, BW_P = 131072, BW_DS = 163840,
               BW_BAR = 196608;
 constexpr int BW_SMEM_TOTAL = BW_BAR + 2048 + 1024;
+constexpr int BW_SM_WARPS = 16;                      // softmax warps: 4 per TMEM lane quadrant, one 32-key chunk each
+constexpr int BW_THREADS = BW_SM_WARPS * 32 + 32;    // + the control warp (TMA + MMA issue)
 
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const AttnBwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_load = (uint64_t*)(smem + BW_BAR);
   uint64_t* bar_sdp = bar_load + 1;   // S and dP of the current pair are in TMEM
-  uint64_t* bar_pds = bar_load + 2;   // P and dS of the current pair are in shared memory (128 arrivals)
+  uint64_t* bar_pds = bar_load + 2;   // P and dS of the current pair are in shared memory (512 arrivals)
   uint64_t* bar_mma2 = bar_load + 3;  // dV/dK/dQ MMAs of the current pair have retired
-  uint64_t* bar_epi = bar_load + 4;   // dK_j/dV_j drained from TMEM (256 arrivals)
+  uint64_t* bar_epi = bar_load + 4;   // dK_j/dV_j drained from TMEM (512 arrivals)
   uint64_t* bar_load1 = bar_load + 5; // operand tiles of sequence block 1 (bar_load: block 0)
   uint32_t* tmem_slot = (uint32_t*)(bar_load + 6);
-  float* s_mask = (float*)(smem + BW_BAR + 64);  // [256] additive key mask
+  uint32_t* s_kbits = (uint32_t*)(smem + BW_BAR + 64);  // [8]: bit t of word w = key 32 w + t is attendable
+  float* s_delta = (float*)(smem + BW_BAR + 128);       // [256] rowsum(dO * O) of this head
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x;
@@ -380,18 +427,50 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(bar_load, 1);
     mbar_init(bar_load1, 1);
     mbar_init(bar_sdp, 1);
-    mbar_init(bar_pds, 256);
+    mbar_init(bar_pds, BW_SM_WARPS * 32);
     mbar_init(bar_mma2, 1);
-    mbar_init(bar_epi, 256);
+    mbar_init(bar_epi, BW_SM_WARPS * 32);
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == BW_SM_WARPS) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+  if (warp < 8) {  // key-padding / sequence-end mask as 8 ballot words
+    const int k = warp * 32 + lane;
     const bool ok = k < p.L && (p.kmask == nullptr || p.kmask[b * p.L + k] != 0);
-    s_mask[k] = ok ? 0.f : -INFINITY;
+    const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_kbits[warp] = bits;
+  }
+  if (warp < BW_SM_WARPS) {
+    // delta[q] = sum_d dO[q, d] O[q, d] (the softmax-backward row term): two threads per row, 32 dims
+    // each; replaces the separate attn_delta pass over O and dO
+    const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+    float acc = 0.f;
+    if (row < p.L) {
+      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + ((long long)row0 + row) * p.E + h * 64 + half * 32);
+      const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + ((long long)row0 + row) * p.E + h * 64 + half * 32);
+      uint4 ov[4], dv4[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        ov[t] = __ldg(o4 + t);
+        dv4[t] = __ldg(d4 + t);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ov[t]);
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv4[t]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[e]));
+          const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[e]));
+          acc = fmaf(a.x, g.x, acc);
+          acc = fmaf(a.y, g.y, acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) s_delta[row] = acc;
   }
   tc_fence_before();
   __syncthreads();
@@ -400,7 +479,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDQ = tmem_base + 256, tDK = tmem_base + 384,
                  tDV = tmem_base + 448;
 
-  if (warp == 8) {
+  if (warp == BW_SM_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_do);
@@ -459,86 +538,85 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     __syncwarp();
   } else {
-    // two threads per query row: warps 0-3 take the even 32-key chunks, warps 4-7 the odd ones
-    // (a warp may only touch TMEM lanes 32*(warp%4) .. +31, any columns). On a diagonal pair
-    // every key of chunk c > warp%4 is in the causal future of all 32 rows of the warp: those
-    // chunks get P = dS = 0 without reading S / dP.
-    const int r = (warp & 3) * 32 + lane;
-    const int ch = warp >> 2;  // column half
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    // FOUR threads per query row: warp w owns TMEM lane quadrant w % 4 (rows 32 (w % 4) .. +31, the
+    // only lanes it may touch) and the 32-key chunk w / 4 of every pair, so the exp / dropout /
+    // pack work of a 128 x 128 pair is spread over 16 warps (4 per scheduler) and every thread
+    // touches S / dP exactly once. On a diagonal pair every key of chunk c > w % 4 is in the
+    // causal future of all 32 rows of the warp: those chunks get P = dS = 0 without reading TMEM.
+    const int qd = warp & 3, c = warp >> 2;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float sl2 = p.scale * LOG2E;
-    uint8_t* prow = smem + BW_P + r * 128;
-    uint8_t* dsrow = smem + BW_DS + r * 128;
+    const int hoff = (c >> 1) * 16384;
+    uint8_t* prow = smem + BW_P + r * 128 + hoff;
+    uint8_t* dsrow = smem + BW_DS + r * 128 + hoff;
     const bool dropping = p.drop_p > 0.f;
     DropKey dk = {0u, 0u, 0u, 1.f};
     if (dropping) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
-    // row statistics of both query blocks, fetched once while the operand tiles are in flight
-    float lse2_blk[2] = {INFINITY, INFINITY}, dl_blk[2] = {0.f, 0.f};  // +inf -> P = 0 beyond the sequence
+    // row statistics of both query blocks (-lse in the exp2 domain; -inf -> P = 0 beyond the sequence)
+    float nlse2_blk[2] = {-INFINITY, -INFINITY}, dl_blk[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int q = i * 128 + r;
       if (i < nb && q < p.L) {
-        const long long so = ((long long)b * p.NH + h) * p.L + q;
-        const float lv = __ldg(p.lse + so);
-        lse2_blk[i] = lv == -INFINITY ? INFINITY : lv * LOG2E;
-        dl_blk[i] = __ldg(p.delta + so);
+        const float lv = __ldg(p.lse + ((long long)b * p.NH + h) * p.L + q);
+        nlse2_blk[i] = lv == -INFINITY ? -INFINITY : -lv * LOG2E;
+        dl_blk[i] = s_delta[q];
       }
     }
     int pair = 0;
     for (int j = 0; j < nb; ++j) {
+      const uint32_t kbits = s_kbits[j * 4 + c];
       for (int i = j; i < nb; ++i, ++pair) {
         const int q = i * 128 + r;
-        const float lse2 = i == 0 ? lse2_blk[0] : lse2_blk[1];
+        const float nlse2 = i == 0 ? nlse2_blk[0] : nlse2_blk[1];
         const float dl = i == 0 ? dl_blk[0] : dl_blk[1];
-        const uint32_t pair_row = (uint32_t)((b * p.NH + h) * p.L + q) * (uint32_t)((p.L + 1) >> 1);
         mbar_wait<25>(bar_sdp, (uint32_t)(pair & 1));
         if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
         tc_fence_after();
-#pragma unroll 1
-        for (int c = ch; c < 4; c += 2) {
-          if (i == j && c > (warp & 3)) {  // warp-uniform
-            const int hoff = (c >> 1) * 16384;
+        if (i == j && c > qd) {  // warp-uniform
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int off = hoff + ((((c & 1) * 4 + t) ^ (r & 7)) << 4);
-              *reinterpret_cast<uint4*>(prow + off) = make_uint4(0u, 0u, 0u, 0u);
-              *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(0u, 0u, 0u, 0u);
-            }
-            continue;
+          for (int t = 0; t < 4; ++t) {
+            const int off = (((c & 1) * 4 + t) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + off) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(0u, 0u, 0u, 0u);
           }
+        } else {
           uint32_t sv[32], dv[32];
           tmem_ld_32x32(tS + lane_addr + c * 32, sv);
           tmem_ld_32x32(tDP + lane_addr + c * 32, dv);
+          // keys this row may attend to inside the chunk: key-padding bits AND the causal limit
+          uint32_t vm = kbits;
+          if (i == j) {
+            const int lim = r - c * 32;  // >= 0 here (c <= qd); key t of the chunk is allowed iff t <= lim
+            if (lim < 31) vm &= (2u << lim) - 1u;
+          }
+          const uint32_t pair0 = (uint32_t)((b * p.NH + h) * p.L + q) * (uint32_t)((p.L + 1) >> 1) +
+                                 (uint32_t)((j * 128 + c * 32) >> 1);
           tmem_ld_wait();
           uint32_t pp[16], pd[16];
 #pragma unroll
           for (int t = 0; t < 32; t += 2) {
-            float pe[2], de[2];
             // with dropout D = keep / (1-p): dV uses P.D, dS = P (D.dP - delta)
-            float dm[2] = {1.f, 1.f};
+            float dm0 = 1.f, dm1 = 1.f;
             if (dropping) {
-              const uint32_t bits = drop_bits(dk, pair_row + (uint32_t)((j * 128 + c * 32 + t) >> 1));
-              dm[0] = drop_keep_lo(dk, bits) ? dk.inv_keep : 0.f;
-              dm[1] = drop_keep_hi(dk, bits) ? dk.inv_keep : 0.f;
+              const uint32_t bits = drop_bits(dk, pair0 + (uint32_t)(t >> 1));
+              dm0 = drop_keep_lo(dk, bits) ? dk.inv_keep : 0.f;
+              dm1 = drop_keep_hi(dk, bits) ? dk.inv_keep : 0.f;
             }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int kc = c * 32 + t + e;
-              const int key = j * 128 + kc;
-              float pv = 0.f;
-              if (key <= q && s_mask[key] == 0.f) pv = exp2f(__uint_as_float(sv[t + e]) * sl2 - lse2);
-              pe[e] = pv * dm[e];
-              de[e] = pv * (__uint_as_float(dv[t + e]) * dm[e] - dl);
-            }
-            __nv_bfloat162 a = __floats2bfloat162_rn(pe[0], pe[1]), d2 = __floats2bfloat162_rn(de[0], de[1]);
+            const float x0 = ((vm >> t) & 1u) ? fmaf(__uint_as_float(sv[t]), sl2, nlse2) : -INFINITY;
+            const float x1 = ((vm >> (t + 1)) & 1u) ? fmaf(__uint_as_float(sv[t + 1]), sl2, nlse2) : -INFINITY;
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            const float pe0 = p0 * dm0, pe1 = p1 * dm1;
+            const float de0 = p0 * fmaf(__uint_as_float(dv[t]), dm0, -dl);
+            const float de1 = p1 * fmaf(__uint_as_float(dv[t + 1]), dm1, -dl);
+            __nv_bfloat162 a = __floats2bfloat162_rn(pe0, pe1), d2 = __floats2bfloat162_rn(de0, de1);
             pp[t >> 1] = *reinterpret_cast<uint32_t*>(&a);
             pd[t >> 1] = *reinterpret_cast<uint32_t*>(&d2);
           }
-          const int hoff = (c >> 1) * 16384;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const int cc = (c & 1) * 4 + t;
-            const int off = hoff + ((cc ^ (r & 7)) << 4);
+            const int off = (((c & 1) * 4 + t) ^ (r & 7)) << 4;
             *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[4 * t], pp[4 * t + 1], pp[4 * t + 2], pp[4 * t + 3]);
             *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(pd[4 * t], pd[4 * t + 1], pd[4 * t + 2], pd[4 * t + 3]);
           }
@@ -547,47 +625,44 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tc_fence_before();
         mbar_arrive(bar_pds);
       }
-      // ---- drain dK_j / dV_j: TMEM lane r = key j*128 + r ----
+      // ---- drain dK_j / dV_j: TMEM lane r = key j*128 + r; chunk 0,1: dK columns, 2,3: dV columns ----
       mbar_wait<27>(bar_mma2, (uint32_t)((pair - 1) & 1));
       tc_fence_after();
       {
         const int key = j * 128 + r;
-        bf16* dst = p.dqkv + ((long long)row0 + key) * 3 * p.E + h * 64;
-#pragma unroll 1
-        for (int c = 2 * ch; c < 2 * ch + 2; ++c) {  // c 0,1 (half 0): dK; c 2,3 (half 1): dV
-          uint32_t v[32];
-          tmem_ld_32x32((c < 2 ? tDK : tDV) + lane_addr + (c & 1) * 32, v);
-          tmem_ld_wait();
-          if (key < p.L) {
-            const float sc = c < 2 ? p.scale : 1.f;
-            bf16* d = dst + (c < 2 ? p.E : 2 * p.E) + (c & 1) * 32;
+        uint32_t v[32];
+        tmem_ld_32x32((c < 2 ? tDK : tDV) + lane_addr + (c & 1) * 32, v);
+        tmem_ld_wait();
+        if (key < p.L) {
+          const float sc = c < 2 ? p.scale : 1.f;
+          bf16* d = p.dqkv + ((long long)row0 + key) * 3 * p.E + h * 64 + (c < 2 ? p.E : 2 * p.E) + (c & 1) * 32;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              uint32_t w[4];
+          for (int t = 0; t < 4; ++t) {
+            uint32_t w[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * sc,
-                                                         __uint_as_float(v[8 * t + 2 * e + 1]) * sc);
-                w[e] = *reinterpret_cast<uint32_t*>(&x);
-              }
-              *reinterpret_cast<uint4*>(d + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * sc,
+                                                       __uint_as_float(v[8 * t + 2 * e + 1]) * sc);
+              w[e] = *reinterpret_cast<uint32_t*>(&x);
             }
+            *reinterpret_cast<uint4*>(d + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(bar_epi);
     }
-    // ---- drain dQ_i (all second-stage MMAs retired: bar_mma2 of the last pair was waited above) ----
-    for (int i = 0; i < nb; ++i) {
-      const int q = i * 128 + r;
-      bf16* dst = p.dqkv + ((long long)row0 + q) * 3 * p.E + h * 64;
-      {
-        const int c = ch;  // each half drains 32 of the 64 dQ columns
+    // ---- drain dQ (all second-stage MMAs retired: bar_mma2 of the last pair was waited above):
+    //      chunk c takes query block c / 2, columns 32 (c % 2) .. +31 ----
+    {
+      const int i = c >> 1;
+      if (i < nb) {  // warp-uniform
+        const int q = i * 128 + r;
         uint32_t v[32];
-        tmem_ld_32x32(tDQ + i * 64 + lane_addr + c * 32, v);
+        tmem_ld_32x32(tDQ + i * 64 + lane_addr + (c & 1) * 32, v);
         tmem_ld_wait();
         if (q < p.L) {
+          bf16* dst = p.dqkv + ((long long)row0 + q) * 3 * p.E + h * 64 + (c & 1) * 32;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             uint32_t w[4];
@@ -597,7 +672,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                                                        __uint_as_float(v[8 * t + 2 * e + 1]) * p.scale);
               w[e] = *reinterpret_cast<uint32_t*>(&x);
             }
-            *reinterpret_cast<uint4*>(dst + c * 32 + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
@@ -605,7 +680,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == BW_SM_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -613,8 +688,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
 }  // namespace
 
-// dqkv for L <= 256; `delta` must already hold rowsum(dO * O) (attn_delta_kernel).
-int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float* lse, const float* delta,
+// dqkv for L <= 256; delta = rowsum(dO * O) is formed inside the kernel from `out` and `dout`.
+int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
                 bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop) {
   MMTG_CHECK_ARG(L <= 256, "tcgen05 attention backward handles L <= 256");
   const int E = NH * 64;
@@ -627,12 +702,12 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float
     attr_set = true;
   }
   AttnBwdTcParams p;
-  p.kmask = kmask; p.lse = lse; p.delta = delta; p.dqkv = dqkv;
+  p.kmask = kmask; p.lse = lse; p.out = out; p.dout = dout; p.dqkv = dqkv;
   p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
   p.drop_seed = drop ? drop->seed : nullptr;
   p.drop_site = drop ? drop->site : 0u;
   p.drop_p = (drop && drop->seed) ? drop->p : 0.f;
-  attn_bwd_tc_kernel<<<B * NH, 288, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
+  attn_bwd_tc_kernel<<<B * NH, BW_THREADS, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;
