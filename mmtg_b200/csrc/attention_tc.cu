@@ -76,11 +76,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_q = (uint64_t*)(smem + SMEM_BAR);
-  uint64_t* bar_kv = bar_q + 1;
+  uint64_t* bar_k = bar_q + 1;
   uint64_t* bar_s = bar_q + 2;
   uint64_t* bar_p = bar_q + 3;
   uint64_t* bar_o = bar_q + 4;
-  uint32_t* tmem_slot = (uint32_t*)(bar_q + 5);
+  uint64_t* bar_v = bar_q + 5;
+  uint32_t* tmem_slot = (uint32_t*)(bar_q + 6);
   uint32_t* s_kbits = (uint32_t*)(smem + SMEM_KBITS);  // bit t of word w: key 32 w + t is attendable
   float* s_red = (float*)(smem + SMEM_RED);            // [2 (block parity)][2 (half)][128 rows]
   float* s_sum = (float*)(smem + SMEM_SUM);            // [2 (half)][128 rows]
@@ -93,15 +94,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
   const int nkv = min(cdiv(p.L, TK), qt + 1);
   const int row0 = b * p.L;  // first row of this batch entry in the [B*L, 3E] matrix
 
-  if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
-    mbar_init(bar_kv, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, FW_SM_WARPS * 32);
-    mbar_init(bar_o, 1);
-    fence_barrier_init();
-  }
   if (warp == FW_SM_WARPS) {
+    // the control warp sets up the barriers and puts Q, K_0 and V_0 in flight before anything else
+    if (lane == 0) {
+      mbar_init(bar_q, 1);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, FW_SM_WARPS * 32);
+      mbar_init(bar_o, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&tm);
+      mbar_arrive_expect_tx(bar_q, TQ * HD * 2);
+      tma_load_2d(smem + SMEM_Q, &tm, bar_q, h * HD, row0 + q0);
+      mbar_arrive_expect_tx(bar_k, TK * HD * 2);
+      tma_load_2d(smem + SMEM_K, &tm, bar_k, p.E + h * HD, row0);
+      mbar_arrive_expect_tx(bar_v, TK * HD * 2);
+      tma_load_2d(smem + SMEM_V, &tm, bar_v, 2 * p.E + h * HD, row0);
+    }
+    __syncwarp();
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -121,40 +132,43 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
   if (warp == FW_SM_WARPS) {
     // ===================== control warp: TMA + MMA =====================
     if (lane == 0) {
-      tma_prefetch_desc(&tm);
-      mbar_arrive_expect_tx(bar_q, TQ * HD * 2);
-      tma_load_2d(smem + SMEM_Q, &tm, bar_q, h * HD, row0 + q0);
       const uint32_t idesc_s = umma_idesc_bf16(128, TK, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
-      const uint32_t aQ = smem_u32(smem + SMEM_Q), aK = smem_u32(smem + SMEM_K);
-      const uint32_t aV = smem_u32(smem + SMEM_V), aP = smem_u32(smem + SMEM_P);
+      // descriptors built once, stepped by immediates (every instruction between two tcgen05.mma
+      // of the single issuing thread is on the critical path)
+      const uint64_t dQ = umma_desc_sw128(smem_u32(smem + SMEM_Q), 16, 1024);
+      const uint64_t dK = umma_desc_sw128(smem_u32(smem + SMEM_K), 16, 1024);
+      const uint64_t dP = umma_desc_sw128(smem_u32(smem + SMEM_P), 16, 1024);
+      const uint64_t dV = umma_desc_sw128(smem_u32(smem + SMEM_V), 8192, 1024);
+      mbar_wait<12>(bar_q, 0);
       for (int j = 0; j < nkv; ++j) {
         ATT_TRACE(10 + 100 * j);
-        if (j > 0) mbar_wait<11>(bar_o, (uint32_t)((j - 1) & 1));  // PV(j-1) retired: K/V/P free
-        ATT_TRACE(11 + 100 * j);
-        mbar_arrive_expect_tx(bar_kv, 2 * TK * HD * 2);
-        tma_load_2d(smem + SMEM_K, &tm, bar_kv, p.E + h * HD, row0 + j * TK);
-        tma_load_2d(smem + SMEM_V, &tm, bar_kv, 2 * p.E + h * HD, row0 + j * TK);
-        if (j == 0) mbar_wait<12>(bar_q, 0);
-        ATT_TRACE(12 + 100 * j);
-        mbar_wait<13>(bar_kv, (uint32_t)(j & 1));
+        mbar_wait<13>(bar_k, (uint32_t)(j & 1));
         ATT_TRACE(13 + 100 * j);
-        tc_fence_after();
+        tc_fence_after();  // (S TMEM is free: bar_p of block j-1 was waited below)
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tS, umma_desc_sw128(aQ + k * 32, 16, 1024), umma_desc_sw128(aK + k * 32, 16, 1024),
-                    idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(bar_s);
         ATT_TRACE(14 + 100 * j);
+        if (j + 1 < nkv) {  // K_j has been consumed once S(j) retires: stream K_{j+1} in under softmax(j)
+          mbar_wait<11>(bar_s, (uint32_t)(j & 1));
+          mbar_arrive_expect_tx(bar_k, TK * HD * 2);
+          tma_load_2d(smem + SMEM_K, &tm, bar_k, p.E + h * HD, row0 + (j + 1) * TK);
+        }
         mbar_wait<14>(bar_p, (uint32_t)(j & 1));  // P written (and O rescaled) by all 128 rows
+        mbar_wait<18>(bar_v, (uint32_t)(j & 1));
         ATT_TRACE(15 + 100 * j);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k)
-          umma_bf16(tO, umma_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    umma_desc_sw128(aV + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tO, dP + (k >> 2) * 1024 + (k & 3) * 2, dV + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar_o);
         ATT_TRACE(16 + 100 * j);
+        if (j + 1 < nkv) {  // V_j / P_j are free once PV(j) retires
+          mbar_wait<19>(bar_o, (uint32_t)(j & 1));
+          mbar_arrive_expect_tx(bar_v, TK * HD * 2);
+          tma_load_2d(smem + SMEM_V, &tm, bar_v, 2 * p.E + h * HD, row0 + (j + 1) * TK);
+        }
       }
     }
     __syncwarp();
@@ -295,27 +309,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p)
     tc_fence_after();
     const float inv = (l_tot > 0.f ? 1.f / l_tot : 0.f) * dk.inv_keep;
     {
-      // tcgen05.ld is .sync.aligned: every lane of the warp loads (rows beyond the sequence
-      // included); only the global stores are predicated
-      bf16* dst = p.out + ((long long)row0 + q) * p.E + h * HD + hf * 32;
+      // O rows leave through a shared-memory transpose (the P tile is idle now): TMEM hands each
+      // thread one row, written directly a warp store would touch 32 different lines; staged, 8
+      // consecutive lanes write one 128-byte row.
       uint32_t v[32];
       tmem_ld_32x32(tO + lane_addr + hf * 32, v);
       tmem_ld_wait();
-      if (q < p.L) {
+      uint8_t* srow = smem + SMEM_P + r * 128;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint32_t w[4];
+      for (int t = 0; t < 4; ++t) {
+        uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * inv,
-                                                     __uint_as_float(v[8 * t + 2 * e + 1]) * inv);
-            w[e] = *reinterpret_cast<uint32_t*>(&x);
-          }
-          *reinterpret_cast<uint4*>(dst + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * inv,
+                                                   __uint_as_float(v[8 * t + 2 * e + 1]) * inv);
+          w[e] = *reinterpret_cast<uint32_t*>(&x);
         }
-        if (hf == 0 && p.lse)
-          p.lse[((long long)b * p.NH + h) * p.L + q] =
-              l_tot > 0.f ? (m_run + log2f(l_tot)) / LOG2E : -INFINITY;
+        *reinterpret_cast<uint4*>(srow + (((hf * 4 + t) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (hf == 0 && q < p.L && p.lse)
+        p.lse[((long long)b * p.NH + h) * p.L + q] = l_tot > 0.f ? (m_run + log2f(l_tot)) / LOG2E : -INFINITY;
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = (int)threadIdx.x + 256 * k, row = idx >> 3, ch = idx & 7;
+        if (q0 + row < p.L) {
+          const uint4 val = *reinterpret_cast<const uint4*>(smem + SMEM_P + row * 128 + ((ch ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(p.out + ((long long)row0 + q0 + row) * p.E + h * HD + ch * 8) = val;
+        }
       }
     }
   }
@@ -392,7 +413,16 @@ struct AttnBwdTcParams {
   const unsigned long long* drop_seed;  // same mask as the forward (see AttnTcParams)
   uint32_t drop_site;
   float drop_p;
+  unsigned long long* clk;  // optional: CTA 0 stamps globaltimer (ns) — [0,32) control thread, [32,64) softmax warp 0
 };
+#define BW_STAMP(slot)                                                        \
+  do {                                                                        \
+    if (p.clk && blockIdx.x == 0 && lane == 0) {                              \
+      unsigned long long t_;                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                  \
+      p.clk[(slot)] = t_;                                                     \
+    }                                                                         \
+  } while (0)
 
 // smem map (bytes): 8 operand tiles of 16 KB, then P and dS (32 KB each), then barriers, key-mask
 // bits and the per-row delta
@@ -401,6 +431,53 @@ constexpr int BW_Q = 0, BW_K = 32768, BW_V = 65536, BW_DO = 98304, BW_P = 131072
 constexpr int BW_SMEM_TOTAL = BW_BAR + 2048 + 1024;
 constexpr int BW_SM_WARPS = 16;                      // softmax warps: 4 per TMEM lane quadrant, one 32-key chunk each
 constexpr int BW_THREADS = BW_SM_WARPS * 32 + 32;    // + the control warp (TMA + MMA issue)
+
+// Drain two 128 x 64 fp32 accumulator tiles (tile = chunk / 2) as bf16 rows of 128 bytes. TMEM hands
+// every thread ONE row (32 columns = 64 bytes): written straight to global memory a warp store would
+// touch 32 different 128-byte lines. The tiles are therefore staged in shared memory (the P region,
+// idle between pairs; 16-byte chunk j of row r at j ^ (r & 7)) and copied out with 8 consecutive
+// lanes per row: every warp store writes four complete lines.
+//   dst(tile, row, col) = gbase + tile * tile_stride + row * pitch + col ; rows >= rows_valid - 128 * tile'
+//   (tile_rows_shared: both tiles cover the same rows) are skipped.
+__device__ __forceinline__ void bw_drain(uint8_t* stage, uint32_t taddr, int r, int c, float scale, uint64_t* bar_free,
+                                         bf16* gbase, long long tile_stride, long long pitch, int rows_valid, int ntiles) {
+  const int tile = c >> 1;
+  if (tile < ntiles) {  // warp-uniform
+    uint32_t v[32];
+    tmem_ld_32x32(taddr, v);
+    tmem_ld_wait();
+    uint8_t* srow = stage + tile * 16384 + r * 128;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * scale,
+                                                 __uint_as_float(v[8 * t + 2 * e + 1]) * scale);
+        w[e] = *reinterpret_cast<uint32_t*>(&x);
+      }
+      *reinterpret_cast<uint4*>(srow + ((((c & 1) * 4 + t) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  if (bar_free) {  // the accumulators are in registers / shared memory: TMEM may be overwritten
+    tc_fence_before();
+    mbar_arrive(bar_free);
+  }
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+  // tile_stride < pitch means "same rows, different columns" (dK | dV); otherwise the tiles are row blocks (dQ_0, dQ_1)
+  const bool same_rows = tile_stride < pitch;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = (int)threadIdx.x + 512 * k;
+    const int tl = idx >> 10, rem = idx & 1023, row = rem >> 3, ch = rem & 7;
+    const int grow = same_rows ? row : tl * 128 + row;
+    if (tl < ntiles && grow < rows_valid) {
+      const uint4 val = *reinterpret_cast<const uint4*>(stage + tl * 16384 + row * 128 + ((ch ^ (row & 7)) << 4));
+      *reinterpret_cast<uint4*>(gbase + tl * tile_stride + (long long)row * pitch + ch * 8) = val;
+    }
+  }
+  asm volatile("bar.sync 1, 512;" ::: "memory");  // the staging area is rewritten by the next pair's P / dS
+}
 
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
@@ -422,17 +499,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int b = bh / p.NH, h = bh - b * p.NH;
   const int nb = cdiv(p.L, 128);  // 1 or 2
   const int row0 = b * p.L;
+  if (warp == 0) BW_STAMP(32);
 
-  if (threadIdx.x == 0) {
-    mbar_init(bar_load, 1);
-    mbar_init(bar_load1, 1);
-    mbar_init(bar_sdp, 1);
-    mbar_init(bar_pds, BW_SM_WARPS * 32);
-    mbar_init(bar_mma2, 1);
-    mbar_init(bar_epi, BW_SM_WARPS * 32);
-    fence_barrier_init();
-  }
   if (warp == BW_SM_WARPS) {
+    // the control warp sets up the barriers and puts all eight operand tiles in flight before anything
+    // else happens: the loads overlap the TMEM allocation and the delta / mask prologue of the other warps
+    if (lane == 0) {
+      mbar_init(bar_load, 1);
+      mbar_init(bar_load1, 1);
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_pds, BW_SM_WARPS * 32);
+      mbar_init(bar_mma2, 1);
+      mbar_init(bar_epi, BW_SM_WARPS * 32);
+      fence_barrier_init();
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      for (int i = 0; i < nb; ++i) {  // block 0 first: its pair can start while block 1 streams in
+        uint64_t* bl = i == 0 ? bar_load : bar_load1;
+        mbar_arrive_expect_tx(bl, (uint32_t)(4 * 16384));
+        tma_load_2d(smem + BW_Q + i * 16384, &tm_qkv, bl, h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_K + i * 16384, &tm_qkv, bl, p.E + h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_V + i * 16384, &tm_qkv, bl, 2 * p.E + h * 64, row0 + i * 128);
+        tma_load_2d(smem + BW_DO + i * 16384, &tm_do, bl, h * 64, row0 + i * 128);
+      }
+    }
+    __syncwarp();
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -478,61 +569,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDQ = tmem_base + 256, tDK = tmem_base + 384,
                  tDV = tmem_base + 448;
+  if (warp == 0) BW_STAMP(33);
 
   if (warp == BW_SM_WARPS) {
+    BW_STAMP(0);
     if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      tma_prefetch_desc(&tm_do);
-      for (int i = 0; i < nb; ++i) {  // block 0 first: its pair can start while block 1 streams in
-        uint64_t* bl = i == 0 ? bar_load : bar_load1;
-        mbar_arrive_expect_tx(bl, (uint32_t)(4 * 16384));
-        tma_load_2d(smem + BW_Q + i * 16384, &tm_qkv, bl, h * 64, row0 + i * 128);
-        tma_load_2d(smem + BW_K + i * 16384, &tm_qkv, bl, p.E + h * 64, row0 + i * 128);
-        tma_load_2d(smem + BW_V + i * 16384, &tm_qkv, bl, 2 * p.E + h * 64, row0 + i * 128);
-        tma_load_2d(smem + BW_DO + i * 16384, &tm_do, bl, h * 64, row0 + i * 128);
-      }
       const uint32_t idesc_sp = umma_idesc_bf16(128, 128, 0, 0);  // S, dP: A K-major, B K-major
       const uint32_t idesc_kv = umma_idesc_bf16(128, 64, 1, 1);   // dV, dK: A (P/dS) MN-major, B MN-major
       const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ: A (dS) K-major, B (K) MN-major
       const uint32_t aP = smem_u32(smem + BW_P), aDS = smem_u32(smem + BW_DS);
+      BW_STAMP(1);
       mbar_wait<21>(bar_load, 0);
+      BW_STAMP(2);
       bool have1 = false;
+      // S = Q_i K_j^T and dP = dO_i V_j^T of one pair. Descriptors are built once and stepped by
+      // immediates (one thread issues every MMA: each instruction in between is on the critical path).
+      auto issue_sdp = [&](int j, int i) {
+        if (i == 1 && !have1) {
+          mbar_wait<24>(bar_load1, 0);
+          have1 = true;
+        }
+        const uint64_t dQk = umma_desc_sw128(smem_u32(smem + BW_Q + i * 16384), 16, 1024);
+        const uint64_t dKk = umma_desc_sw128(smem_u32(smem + BW_K + j * 16384), 16, 1024);
+        const uint64_t dOk = umma_desc_sw128(smem_u32(smem + BW_DO + i * 16384), 16, 1024);
+        const uint64_t dVk = umma_desc_sw128(smem_u32(smem + BW_V + j * 16384), 16, 1024);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS, dQk + 2 * k, dKk + 2 * k, idesc_sp, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tDP, dOk + 2 * k, dVk + 2 * k, idesc_sp, k > 0 ? 1u : 0u);
+        umma_commit(bar_sdp);
+      };
+      issue_sdp(0, 0);
+      BW_STAMP(3);
       int pair = 0;
       for (int j = 0; j < nb; ++j) {
-        const uint32_t aK = smem_u32(smem + BW_K + j * 16384), aV = smem_u32(smem + BW_V + j * 16384);
+        const uint32_t aK = smem_u32(smem + BW_K + j * 16384);
         for (int i = j; i < nb; ++i, ++pair) {
           const uint32_t aQ = smem_u32(smem + BW_Q + i * 16384), aDO = smem_u32(smem + BW_DO + i * 16384);
-          if (i == 1 && !have1) {
-            mbar_wait<24>(bar_load1, 0);
-            have1 = true;
-          }
-          // S/dP TMEM is free once the softmax threads have consumed the previous pair (bar_pds
-          // of pair-1, waited below before the second-stage MMAs of that pair were issued).
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tS, umma_desc_sw128(aQ + k * 32, 16, 1024), umma_desc_sw128(aK + k * 32, 16, 1024),
-                      idesc_sp, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tDP, umma_desc_sw128(aDO + k * 32, 16, 1024), umma_desc_sw128(aV + k * 32, 16, 1024),
-                      idesc_sp, k > 0 ? 1u : 0u);
-          umma_commit(bar_sdp);
-          if (i == j && j > 0) mbar_wait<22>(bar_epi, (uint32_t)((j - 1) & 1));  // dK/dV of j-1 drained
+          // softmax(pair) has consumed S / dP and written P / dS (the dK/dV drain of key block j-1,
+          // which precedes it in the softmax threads' program order, is complete as well)
           mbar_wait<23>(bar_pds, (uint32_t)(pair & 1));
+          BW_STAMP(4 + pair * 3);
+          const uint64_t dPm = umma_desc_sw128(aP, 16384, 1024), dSm = umma_desc_sw128(aDS, 16384, 1024);  // MN-major A
+          const uint64_t dOm = umma_desc_sw128(aDO, 8192, 1024), dQm = umma_desc_sw128(aQ, 8192, 1024);    // MN-major B
+          const uint64_t dKm = umma_desc_sw128(aK, 8192, 1024), dSk = umma_desc_sw128(aDS, 16, 1024);
           tc_fence_after();
+          const uint32_t acc_kv = i > j ? 1u : 0u, acc_q = j > 0 ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // reduction over the 128 query rows of block i
-            const uint64_t dP_ = umma_desc_sw128(aP + k * 2048, 16384, 1024);
-            const uint64_t dDS = umma_desc_sw128(aDS + k * 2048, 16384, 1024);
-            umma_bf16(tDV, dP_, umma_desc_sw128(aDO + k * 2048, 8192, 1024), idesc_kv, (i > j || k > 0) ? 1u : 0u);
-            umma_bf16(tDK, dDS, umma_desc_sw128(aQ + k * 2048, 8192, 1024), idesc_kv, (i > j || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {  // reduction over the 128 query rows of block i (2048-byte steps)
+            umma_bf16(tDV, dPm + 128 * k, dOm + 128 * k, idesc_kv, k > 0 ? 1u : acc_kv);
+            umma_bf16(tDK, dSm + 128 * k, dQm + 128 * k, idesc_kv, k > 0 ? 1u : acc_kv);
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // reduction over the 128 keys of block j
-            umma_bf16(tDQ + i * 64, umma_desc_sw128(aDS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      umma_desc_sw128(aK + k * 2048, 8192, 1024), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tDQ + i * 64, dSk + (k >> 2) * 1024 + (k & 3) * 2, dKm + 128 * k, idesc_dq, k > 0 ? 1u : acc_q);
           umma_commit(bar_mma2);
+          BW_STAMP(5 + pair * 3);
+          // S / dP of the next pair queue right behind (measured: issuing them AHEAD of the gradient
+          // MMAs gains nothing - the pair is bound by the tensor pipe's shared-memory operand reads)
+          const int ni = i + 1 < nb ? i + 1 : j + 1, nj = i + 1 < nb ? j : j + 1;
+          if (nj < nb) issue_sdp(nj, ni);
         }
       }
     }
@@ -571,10 +668,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const int q = i * 128 + r;
         const float nlse2 = i == 0 ? nlse2_blk[0] : nlse2_blk[1];
         const float dl = i == 0 ? dl_blk[0] : dl_blk[1];
+        if (warp == 0) BW_STAMP(34 + pair * 5);
         mbar_wait<25>(bar_sdp, (uint32_t)(pair & 1));
-        if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
+        if (warp == 0) BW_STAMP(35 + pair * 5);
         tc_fence_after();
         if (i == j && c > qd) {  // warp-uniform
+          if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));  // P/dS smem free again
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int off = (((c & 1) * 4 + t) ^ (r & 7)) << 4;
@@ -594,6 +693,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           const uint32_t pair0 = (uint32_t)((b * p.NH + h) * p.L + q) * (uint32_t)((p.L + 1) >> 1) +
                                  (uint32_t)((j * 128 + c * 32) >> 1);
           tmem_ld_wait();
+          if (warp == 0) BW_STAMP(37 + pair * 5);
           uint32_t pp[16], pd[16];
 #pragma unroll
           for (int t = 0; t < 32; t += 2) {
@@ -614,6 +714,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             pp[t >> 1] = *reinterpret_cast<uint32_t*>(&a);
             pd[t >> 1] = *reinterpret_cast<uint32_t*>(&d2);
           }
+          // P / dS of the previous pair are still being read by its dV / dK / dQ MMAs, which run
+          // concurrently with the arithmetic above: wait for them only now
+          if (pair > 0) mbar_wait<26>(bar_mma2, (uint32_t)((pair - 1) & 1));
+          if (warp == 0) BW_STAMP(36 + pair * 5);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int off = (((c & 1) * 4 + t) ^ (r & 7)) << 4;
@@ -624,69 +728,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_pds);
+        if (warp == 0) BW_STAMP(38 + pair * 5);
       }
       // ---- drain dK_j / dV_j: TMEM lane r = key j*128 + r; chunk 0,1: dK columns, 2,3: dV columns ----
       mbar_wait<27>(bar_mma2, (uint32_t)((pair - 1) & 1));
       tc_fence_after();
-      {
-        const int key = j * 128 + r;
-        uint32_t v[32];
-        tmem_ld_32x32((c < 2 ? tDK : tDV) + lane_addr + (c & 1) * 32, v);
-        tmem_ld_wait();
-        if (key < p.L) {
-          const float sc = c < 2 ? p.scale : 1.f;
-          bf16* d = p.dqkv + ((long long)row0 + key) * 3 * p.E + h * 64 + (c < 2 ? p.E : 2 * p.E) + (c & 1) * 32;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * sc,
-                                                       __uint_as_float(v[8 * t + 2 * e + 1]) * sc);
-              w[e] = *reinterpret_cast<uint32_t*>(&x);
-            }
-            *reinterpret_cast<uint4*>(d + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_epi);
+      bw_drain(smem + BW_P, (c < 2 ? tDK : tDV) + lane_addr + (c & 1) * 32, r, c, c < 2 ? p.scale : 1.f, bar_epi,
+               p.dqkv + ((long long)row0 + j * 128) * 3 * p.E + h * 64 + p.E, p.E, 3 * p.E, p.L - j * 128, 2);
+      if (warp == 0) BW_STAMP(50 + j * 2);
     }
     // ---- drain dQ (all second-stage MMAs retired: bar_mma2 of the last pair was waited above):
     //      chunk c takes query block c / 2, columns 32 (c % 2) .. +31 ----
-    {
-      const int i = c >> 1;
-      if (i < nb) {  // warp-uniform
-        const int q = i * 128 + r;
-        uint32_t v[32];
-        tmem_ld_32x32(tDQ + i * 64 + lane_addr + (c & 1) * 32, v);
-        tmem_ld_wait();
-        if (q < p.L) {
-          bf16* dst = p.dqkv + ((long long)row0 + q) * 3 * p.E + h * 64 + (c & 1) * 32;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(v[8 * t + 2 * e]) * p.scale,
-                                                       __uint_as_float(v[8 * t + 2 * e + 1]) * p.scale);
-              w[e] = *reinterpret_cast<uint32_t*>(&x);
-            }
-            *reinterpret_cast<uint4*>(dst + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
-      }
-    }
+    bw_drain(smem + BW_P, tDQ + (c >> 1) * 64 + lane_addr + (c & 1) * 32, r, c, p.scale, nullptr,
+             p.dqkv + (long long)row0 * 3 * p.E + h * 64, (long long)128 * 3 * p.E, 3 * p.E, p.L, nb);
   }
+  if (warp == 0) BW_STAMP(60);
   tc_fence_before();
   __syncthreads();
   if (warp == BW_SM_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (warp == 0) BW_STAMP(61);
 }
 
 }  // namespace
+
+static unsigned long long* g_attn_clk = nullptr;
+void attn_set_clk(unsigned long long* dev) { g_attn_clk = dev; }
 
 // dqkv for L <= 256; delta = rowsum(dO * O) is formed inside the kernel from `out` and `dout`.
 int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
@@ -707,6 +776,7 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* 
   p.drop_seed = drop ? drop->seed : nullptr;
   p.drop_site = drop ? drop->site : 0u;
   p.drop_p = (drop && drop->seed) ? drop->p : 0.f;
+  p.clk = g_attn_clk;
   attn_bwd_tc_kernel<<<B * NH, BW_THREADS, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
   MMTG_LAUNCH_OK();
   count_launch();
@@ -717,3 +787,5 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* 
 
 // debugging aid: progress trace into host-mapped (pinned) memory, readable while a kernel hangs
 extern "C" void mmtg_attn_set_trace(int32_t* host_mapped) { mmtg::attn_set_trace(host_mapped); }
+// debugging aid: CTA 0 of the tcgen05 attention backward stamps globaltimer into dev_buf (>= 64 entries)
+extern "C" void mmtg_attn_set_clk(uint64_t* dev_buf) { mmtg::attn_set_clk((unsigned long long*)dev_buf); }

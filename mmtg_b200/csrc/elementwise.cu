@@ -174,6 +174,132 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
 }
 
 // ------------------------------------------------------------------------------------------
+// LayerNorm backward of the decoder's residual stream, split in two (E = 768, bf16 dy):
+//  * ln_bwd_rows_kernel - the part the backward CHAIN waits for: one warp per row, the row lives in
+//    registers (x, dy, the running residual gradient: 18 independent 8/16-byte loads per lane are
+//    in flight before the first use), dx += rstd (g - mean(g) - xhat mean(g xhat)) and its masked
+//    bf16 copy are written once. No column accumulators, no atomics: 16 bytes per element.
+//  * ln_param_grad_kernel - dgamma, dbeta and the column sums of the bf16 dx copy (the bias
+//    gradient of the c_proj that feeds this LayerNorm's input): column-oriented partial sums
+//    over a row range. Only the optimizer consumes them, so the engine runs this kernel on the
+//    weight-gradient side stream.
+// ------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(128)
+ln_bwd_rows_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dx,
+                   int accumulate_dx, bf16* __restrict__ dx16, int M,
+                   const unsigned long long* __restrict__ drop_seed, uint32_t drop_site, float drop_p, int drop_dx32) {
+  constexpr int V = E / 128;  // float4 per lane
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int l = lane_id();
+  const long long base = (long long)row * E;
+  float4 xv[V], old[V];
+  uint2 dyv[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c4 = l + i * 32;
+    xv[i] = __ldg(reinterpret_cast<const float4*>(x + base) + c4);
+    dyv[i] = __ldg(reinterpret_cast<const uint2*>(dy + base) + c4);
+    if (accumulate_dx) old[i] = *(reinterpret_cast<const float4*>(dx + base) + c4);
+  }
+  const float mu = mean[row], rs = rstd[row];
+  const bool dropping = drop_p > 0.f;
+  DropKey dk = {0u, 0u, 0u, 1.f};
+  if (dropping) dk = drop_key(drop_seed, drop_site, drop_p);
+  float4 g[V];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + l + i * 32);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dyv[i].x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dyv[i].y));
+    g[i] = make_float4(a.x * gm.x, a.y * gm.y, b.x * gm.z, b.y * gm.w);
+    xv[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);  // xhat
+    s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+    s2 += g[i].x * xv[i].x + g[i].y * xv[i].y + g[i].z * xv[i].z + g[i].w * xv[i].w;
+  }
+  const float m1 = warp_sum(s1) * (1.f / E), m2 = warp_sum(s2) * (1.f / E);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c4 = l + i * 32;
+    float4 o;
+    o.x = rs * (g[i].x - m1 - xv[i].x * m2);
+    o.y = rs * (g[i].y - m1 - xv[i].y * m2);
+    o.z = rs * (g[i].z - m1 - xv[i].z * m2);
+    o.w = rs * (g[i].w - m1 - xv[i].w * m2);
+    if (accumulate_dx) {
+      o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w;
+    }
+    float4 om = o;
+    if (dropping) {  // dx16 carries dx * mask / (1 - p) (see ln_bwd_kernel)
+      const uint32_t pair = (uint32_t)((base + c4 * 4) >> 1);
+      const uint32_t b0 = drop_bits(dk, pair), b1 = drop_bits(dk, pair + 1);
+      om.x = drop_keep_lo(dk, b0) ? o.x * dk.inv_keep : 0.f;
+      om.y = drop_keep_hi(dk, b0) ? o.y * dk.inv_keep : 0.f;
+      om.z = drop_keep_lo(dk, b1) ? o.z * dk.inv_keep : 0.f;
+      om.w = drop_keep_hi(dk, b1) ? o.w * dk.inv_keep : 0.f;
+    }
+    *(reinterpret_cast<float4*>(dx + base) + c4) = drop_dx32 ? om : o;
+    if (dx16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(om.x, om.y), hi = __floats2bfloat162_rn(om.z, om.w);
+      *(reinterpret_cast<uint2*>(dx16 + base) + c4) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
+// grid = (E / 128, row splits); each warp owns 128 columns (4 per lane) of a row subset
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const bf16* __restrict__ dx16, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dx_colsum, int M, int E) {
+  __shared__ float4 part[3][8][32];
+  const int warp = threadIdx.x >> 5, l = lane_id();
+  const int col = blockIdx.x * 128 + l * 4;
+  const int rows_per = cdiv(M, (int)gridDim.y);
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float4 adg = make_float4(0.f, 0.f, 0.f, 0.f), adb = adg, acs = adg;
+#pragma unroll 4
+  for (int r = r0 + warp; r < r1; r += 8) {
+    const long long off = (long long)r * E + col;
+    const uint2 du = __ldg(reinterpret_cast<const uint2*>(dy + off));
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + off));
+    uint2 cu = make_uint2(0u, 0u);
+    if (dx16) cu = __ldg(reinterpret_cast<const uint2*>(dx16 + off));
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.x));
+    const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.y));
+    const float2 c0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cu.x));
+    const float2 c1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cu.y));
+    adg.x += d0.x * (xv.x - mu) * rs; adg.y += d0.y * (xv.y - mu) * rs;
+    adg.z += d1.x * (xv.z - mu) * rs; adg.w += d1.y * (xv.w - mu) * rs;
+    adb.x += d0.x; adb.y += d0.y; adb.z += d1.x; adb.w += d1.y;
+    acs.x += c0.x; acs.y += c0.y; acs.z += c1.x; acs.w += c1.y;
+  }
+  part[0][warp][l] = adg;
+  part[1][warp][l] = adb;
+  part[2][warp][l] = acs;
+  __syncthreads();
+  if (warp < 3) {
+    float4 t = part[warp][0][l];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 u = part[warp][w][l];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* out = warp == 0 ? dgamma : (warp == 1 ? dbeta : dx_colsum);
+    if (out) {
+      atomicAdd(out + col, t.x);
+      atomicAdd(out + col + 1, t.y);
+      atomicAdd(out + col + 2, t.z);
+      atomicAdd(out + col + 3, t.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // fp32 -> bf16 cast (weights, activations), 8 elements per thread.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -373,6 +499,15 @@ int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean
   const float dp = (drop && drop->seed) ? drop->p : 0.f;
   const int ddx32 = drop ? drop->mask_dx32 : 0;
   MMTG_CHECK_ARG(E == 768 || E == 512, "LayerNorm width %d not instantiated (512, 768)", E);
+  if (E == 768 && dy_bf16 && !dgamma && !dbeta && !dx_colsum) {
+    // chain part only (the parameter gradients come from ln_param_grads on the side stream)
+    ProfScope prof(2, 0, (double)M * E * (4 + 2 + 4 + (accumulate_dx ? 4 : 0) + (dx16 ? 2 : 0)), st);
+    ln_bwd_rows_kernel<768><<<cdiv(M, 4), 128, 0, st>>>((const bf16*)dy, x, mean, rstd, gamma, dx, accumulate_dx, dx16, M,
+                                                        dseed, dsite, dp, ddx32);
+    MMTG_LAUNCH_OK();
+    count_launch();
+    return 0;
+  }
   // 3 blocks of E/2 threads are resident per SM (56 registers): one balanced wave
   const int blocks = max(1, min(M, num_sms() * 3));
   ProfScope prof(2, 0, (double)M * E * (4 + (dy_bf16 ? 2 : 4) + 4 + (accumulate_dx ? 4 : 0) + (dx16 ? 2 : 0)), st);
@@ -380,6 +515,19 @@ int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean
   if (E == 768) { if (dy_bf16) LNB(768, true); else LNB(768, false); }
   else { if (dy_bf16) LNB(512, true); else LNB(512, false); }
 #undef LNB
+  MMTG_LAUNCH_OK();
+  count_launch();
+  return 0;
+}
+
+int ln_param_grads(const bf16* dy, const float* x, const float* mean, const float* rstd, const bf16* dx16,
+                   float* dgamma, float* dbeta, float* dx_colsum, int M, int E, cudaStream_t st) {
+  MMTG_CHECK_ARG(E % 128 == 0, "ln_param_grads needs E %% 128 == 0");
+  int splits = cdiv(num_sms() * 4, E / 128);
+  splits = max(1, min(splits, cdiv(M, 32)));
+  dim3 grid(E / 128, splits);
+  ProfScope prof(2, 0, (double)M * E * (2 + 4 + (dx16 ? 2 : 0)), st);
+  ln_param_grad_kernel<<<grid, 256, 0, st>>>(dy, x, mean, rstd, dx16, dgamma, dbeta, dx_colsum, M, E);
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;

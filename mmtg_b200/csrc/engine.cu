@@ -50,7 +50,7 @@ struct Ws {
   // decoder backward
   bf16* dlogits16;
   float* dh;
-  bf16 *g16x[2], *g16b, *du, *dx, *datt, *dqkv, *dp1, *dE;  // g16x: ping-pong by backward stage parity
+  bf16 *g16x[2], *g16b[2], *du[2], *dx[2], *dx2[2], *datt[2], *dqkv[2], *dp1, *dE;  // [2]: ping-pong by backward stage parity
   float* delta;
   // encoder forward
   bf16 *x_topic16, *x_mod16[2];
@@ -127,11 +127,16 @@ void carve(const mmtg_dims& d, uint8_t* base, Ws* w) {
   w->dh = f32(M * E);
   w->g16x[0] = b16(M * E);
   w->g16x[1] = b16(M * E);
-  w->g16b = b16(M * E);
-  w->du = b16(M * 4 * E);
-  w->dx = b16(M * E);
-  w->datt = b16(M * E);
-  w->dqkv = b16(M * 3 * E);
+  // every per-stage temporary exists twice: the side-stream work of stage s (weight / parameter
+  // gradients reading these buffers) may still run while the chain of stage s + 1 writes the others
+  for (int k = 0; k < 2; ++k) {
+    w->g16b[k] = b16(M * E);
+    w->du[k] = b16(M * 4 * E);
+    w->dx[k] = b16(M * E);
+    w->dx2[k] = b16(M * E);
+    w->datt[k] = b16(M * E);
+    w->dqkv[k] = b16(M * 3 * E);
+  }
   w->dp1 = b16(M * He);
   w->dE = b16(M * Dw);
   w->delta = f32((size_t)d.B * d.NH * d.L);
@@ -415,6 +420,7 @@ namespace {
 struct SideStream {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t done[2] = {nullptr, nullptr};  // side work of the backward stages of either parity
   bool used = false;
 };
 int g_side_enabled = -1;  // -1: from MMTG_WGRAD_STREAM (default on); 0 / 1: mmtg_set_wgrad_side_stream
@@ -433,7 +439,9 @@ SideStream* side_stream() {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.done[1], cudaEventDisableTiming) != cudaSuccess)
       return nullptr;
   }
   return &s;
@@ -479,11 +487,24 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
     ss->used = true;
     return fn(ss->side);
   };
-  auto join_side = [&]() -> int {
+  // The side-stream work of stage s is joined ONE STAGE LATE: all per-stage temporaries are
+  // double-buffered by stage parity, so the only buffer stage s + 1 writes that the side work of
+  // stage s still reads is g16x[s & 1] (its g_in), rewritten by the LAST kernel of stage s + 1.
+  // Joining at every stage end put the tail of the side work (the kernels forked last) on the
+  // critical chain.
+  bool pending[2] = {false, false};
+  auto stage_done = [&](int stage) -> int {  // end of a stage: mark where its side work ends
     if (ss && ss->used) {
-      MMTG_CUDA_OK(cudaEventRecord(ss->join, ss->side));
-      MMTG_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+      MMTG_CUDA_OK(cudaEventRecord(ss->done[stage & 1], ss->side));
+      pending[stage & 1] = true;
       ss->used = false;
+    }
+    return 0;
+  };
+  auto wait_side_of = [&](int stage) -> int {  // the chain waits for the side work of `stage`
+    if (ss && stage >= 0 && pending[stage & 1]) {
+      MMTG_CUDA_OK(cudaStreamWaitEvent(st, ss->done[stage & 1], 0));
+      pending[stage & 1] = false;
     }
     return 0;
   };
@@ -491,17 +512,25 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
   for (int stage = stage_begin; stage < stage_end; ++stage) {
     bf16* g_in = w.g16x[stage & 1];         // bf16 gradient of this stage's input (from the stage before)
     bf16* g_out = w.g16x[(stage + 1) & 1];  // ... emitted for the next stage
+    const int sp = stage & 1;
+    bf16 *t_du = w.du[sp], *t_dx = w.dx[sp], *t_dx2 = w.dx2[sp], *t_g16b = w.g16b[sp], *t_datt = w.datt[sp],
+         *t_dqkv = w.dqkv[sp];
+    if (stage > d.NL) MMTG_TRY(wait_side_of(stage - 1));  // (embedding / encoder stages: simply at their start)
     if (stage == 0) {
       // ---------------- lm_head (tied wte) + ln_f ----------------
       // dxf = dlogits · wte  (B operand: wte [V,E] as MN-major [N=E, K=V])
-      MMTG_TRY(Gemm(w.dlogits16, d.Vp, false, W + o.wte, E, true, M, E, d.V).out_bf16(w.dx, E).run(st));
+      MMTG_TRY(Gemm(w.dlogits16, d.Vp, false, W + o.wte, E, true, M, E, d.V).out_bf16(t_dx, E).run(st));
       // dwte += dlogits^T · xf
       MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(w.dlogits16, d.Vp, w.xf, E, G + o.wte, E, d.V, E, M, s2, wg); }));
       // also emits g16 = bf16(dh) and the mlp c_proj bias gradient of the top block
       // (masked by the top block's mlp resid dropout: g16 is the gradient of the c_proj OUTPUT)
       const DropSpec dr = drop_spec(m, 4u * (d.NL - 1) + 2, m->p_resid);
-      MMTG_TRY(layernorm_bwd(w.dx, 1, w.layer[d.NL - 1].h_out, w.meanf, w.rstdf, P + o.lnf_w, w.dh, 0,
-                             G + o.lnf_w, G + o.lnf_b, g_out, G + o.layer[d.NL - 1].proj2_b, M, E, st, &dr));
+      MMTG_TRY(layernorm_bwd(t_dx, 1, w.layer[d.NL - 1].h_out, w.meanf, w.rstdf, P + o.lnf_w, w.dh, 0,
+                             nullptr, nullptr, g_out, nullptr, M, E, st, &dr));
+      MMTG_TRY(on_side([&](cudaStream_t s2) {
+        return ln_param_grads(t_dx, w.layer[d.NL - 1].h_out, w.meanf, w.rstdf, g_out, G + o.lnf_w, G + o.lnf_b,
+                              G + o.layer[d.NL - 1].proj2_b, M, E, s2);
+      }));
     } else if (stage <= d.NL) {
       const int l = d.NL - stage;
       const LayerWs& L = w.layer[l];
@@ -511,33 +540,41 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       // (the c_fc bias gradient = column sums of du is a separate HBM-bound pass on the side
       // stream: fused into this epilogue it cost 13 us of the critical chain, measured)
       MMTG_TRY(Gemm(g_in, E, false, W + lo.proj2_w, E, false, M, 4 * E, E)
-                   .out_bf16(w.du, 4 * E).dmul(L.u, 4 * E).run(st));
+                   .out_bf16(t_du, 4 * E).dmul(L.u, 4 * E).run(st));
       MMTG_TRY(on_side([&](cudaStream_t s2) {
-        MMTG_TRY(colsum(w.du, 1, 4 * E, nullptr, 0, G + lo.fc_b, M, 4 * E, s2));
-        return wgrad(L.x2, E, w.du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, s2, wg);
+        MMTG_TRY(colsum(t_du, 1, 4 * E, nullptr, 0, G + lo.fc_b, M, 4 * E, s2));
+        return wgrad(L.x2, E, t_du, 4 * E, G + lo.fc_w, 4 * E, E, 4 * E, M, s2, wg);
       }));
-      MMTG_TRY(Gemm(w.du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(w.dx, E).run(st));
+      MMTG_TRY(Gemm(t_du, 4 * E, false, W + lo.fc_w, 4 * E, false, M, E, 4 * E).out_bf16(t_dx, E).run(st));
       const DropSpec d_att = drop_spec(m, 4u * l, m->p_attn), d_r1 = drop_spec(m, 4u * l + 1, m->p_resid);
-      MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_mid, L.mean2, L.rstd2, P + lo.ln2_w, w.dh, 1, G + lo.ln2_w,
-                             G + lo.ln2_b, w.g16b, G + lo.proj_b, M, E, st, &d_r1));
-      // ---- attention ----
-      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.att, E, w.g16b, E, G + lo.proj_w, E, E, E, M, s2, wg); }));
-      MMTG_TRY(Gemm(w.g16b, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(w.datt, E).run(st));
-      MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, w.datt, L.lse, w.delta, w.dqkv, B, d.L, d.NH, st, &d_att));
+      // (dgamma / dbeta / the c_proj bias gradient only feed the optimizer: side stream)
+      MMTG_TRY(layernorm_bwd(t_dx, 1, L.h_mid, L.mean2, L.rstd2, P + lo.ln2_w, w.dh, 1, nullptr, nullptr, t_g16b,
+                             nullptr, M, E, st, &d_r1));
       MMTG_TRY(on_side([&](cudaStream_t s2) {
-        MMTG_TRY(colsum(w.dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, s2));
-        return wgrad(L.x1, E, w.dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, s2, wg);
+        return ln_param_grads(t_dx, L.h_mid, L.mean2, L.rstd2, t_g16b, G + lo.ln2_w, G + lo.ln2_b, G + lo.proj_b, M, E, s2);
       }));
-      MMTG_TRY(Gemm(w.dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(w.dx, E).run(st));
+      // ---- attention ----
+      MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.att, E, t_g16b, E, G + lo.proj_w, E, E, E, M, s2, wg); }));
+      MMTG_TRY(Gemm(t_g16b, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(t_datt, E).run(st));
+      MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, t_datt, L.lse, w.delta, t_dqkv, B, d.L, d.NH, st, &d_att));
+      MMTG_TRY(on_side([&](cudaStream_t s2) {
+        MMTG_TRY(colsum(t_dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, s2));
+        return wgrad(L.x1, E, t_dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, s2, wg);
+      }));
+      MMTG_TRY(Gemm(t_dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(t_dx2, E).run(st));
       // dh is now the gradient of this block's input: its bf16 copy / column sums feed the block
       // below (mlp c_proj bias) or, for block 0, the projector (projector_layer2 bias)
       // (masked by the dropout that produced this block's input: the mlp resid dropout of the
       // block below, or the embedding dropout — there the fp32 dh is masked too)
       const DropSpec d_in = l > 0 ? drop_spec(m, 4u * (l - 1) + 2, m->p_resid)
                                   : drop_spec(m, MMTG_DROP_SITE_EMBD, m->p_embd, 1);
-      MMTG_TRY(layernorm_bwd(w.dx, 1, L.h_in, L.mean1, L.rstd1, P + lo.ln1_w, w.dh, 1, G + lo.ln1_w,
-                             G + lo.ln1_b, g_out, l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, st,
-                             &d_in));
+      MMTG_TRY(wait_side_of(stage - 1));  // g_out below is the g_in the side work of the previous stage read
+      MMTG_TRY(layernorm_bwd(t_dx2, 1, L.h_in, L.mean1, L.rstd1, P + lo.ln1_w, w.dh, 1, nullptr, nullptr, g_out,
+                             nullptr, M, E, st, &d_in));
+      MMTG_TRY(on_side([&](cudaStream_t s2) {
+        return ln_param_grads(t_dx2, L.h_in, L.mean1, L.rstd1, g_out, G + lo.ln1_w, G + lo.ln1_b,
+                              l > 0 ? G + o.layer[l - 1].proj2_b : G + o.proj2_b, M, E, s2);
+      }));
     } else if (stage == d.NL + 1) {
       // ---------------- embeddings + projector ----------------
       MMTG_TRY(posadd_bwd(w.dh, G + o.wpe, B, d.L, E, st));
@@ -594,9 +631,11 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
                          3 * He, He, (S - 1) * B, st));
       }
     }
-    // side-stream weight gradients of this stage are complete before the next stage reuses
-    // du / dqkv / g16 (and before the caller all-reduces this stage's gradient bucket)
-    MMTG_TRY(join_side());
+    MMTG_TRY(stage_done(stage));
   }
+  // all side-stream work is complete when the call returns (the caller may all-reduce the
+  // gradient buckets of these stages, and a stream capture must end fully joined)
+  MMTG_TRY(wait_side_of(stage_end - 1));
+  MMTG_TRY(wait_side_of(stage_end - 2));
   return 0;
 }

@@ -61,6 +61,11 @@ struct GemmParams {
   uint32_t drop_site;
   float drop_p;
   int grid_mode;
+  // tail split (F_TAIL): work units [0, tail_full) are whole tiles; each tile >= tail_full is cut into
+  // tail_S k-slices of tail_kbs k-blocks (slice 0 owns the epilogue and adds the others' partials)
+  int tail_full, tail_S, tail_kbs, tail_total;
+  float* tail_ws;            // [tail tile][slice - 1][cta rank][128][BN] fp32 partial accumulators
+  unsigned int* tail_flags;  // [2][tail tile]: arrivals of the partial slices / owner warps done
 };
 
 // TWO = cta_group::2: the pair's 256 x BN tile is ONE MMA; each CTA stages its own 128 A rows and
@@ -87,8 +92,36 @@ struct GemmCfg {
 // epilogue feature bits (compile-time mask EPI)
 enum : uint32_t {
   F_OUT2 = 1, F_ACT = 2, F_DACT = 4, F_RES = 8, F_ROWTAB = 16, F_COLSUM = 32, F_ATOMIC = 64,
-  F_LSE = 128, F_SCALAR = 256, F_DROP = 512
+  F_LSE = 128, F_SCALAR = 256, F_DROP = 512, F_TAIL = 1024
 };
+
+// One work item of a cluster: tile index, k-block range, and (tail split) which slice of how many.
+struct WorkUnit {
+  int tile, kb0, kb1, slice, nsl;
+};
+template <uint32_t EPI>
+__device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int w) {
+  WorkUnit u;
+  if constexpr (EPI & F_TAIL) {
+    if (w < p.tail_full) {
+      u.tile = w; u.kb0 = 0; u.kb1 = p.num_kb; u.slice = 0; u.nsl = 1;
+    } else {
+      const int t = w - p.tail_full;
+      u.tile = p.tail_full + t / p.tail_S;
+      u.slice = t - (u.tile - p.tail_full) * p.tail_S;
+      u.kb0 = u.slice * p.tail_kbs;
+      u.kb1 = min(p.num_kb, u.kb0 + p.tail_kbs);
+      u.nsl = p.tail_S;
+    }
+  } else {
+    u.tile = w / p.splits;
+    u.slice = w - u.tile * p.splits;
+    u.kb0 = u.slice * p.kb_per_split;
+    u.kb1 = min(p.num_kb, u.kb0 + p.kb_per_split);
+    u.nsl = 1;  // (uniform split-K combines through atomics, not through the fix-up)
+  }
+  return u;
+}
 
 template <int BN, uint32_t EPI, bool TWO>
 __global__ void __launch_bounds__(320, 1)
@@ -151,18 +184,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const uint32_t crank = cluster_ctarank();       // 0 / 1 within the pair
   const int cluster_id = blockIdx.x >> 1;
   const int nclusters = gridDim.x >> 1;
-  const int total = p.num_mp * p.num_n * p.splits;  // work units of a PAIR
+  const int total = (EPI & F_TAIL) ? p.tail_total : p.num_mp * p.num_n * p.splits;  // work units of a PAIR
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int s = 0;
     uint32_t ph = 0;
     for (int w = cluster_id; w < total; w += nclusters) {
-      const int tile = w / p.splits, ks = w - tile * p.splits;
+      const WorkUnit wu = decode_unit<EPI>(p, w);
+      const int tile = wu.tile;
       const int n_t = tile / p.num_mp, m_t = (tile - n_t * p.num_mp) * 2 + (int)crank;
       const int m0 = m_t * C::BM, n0 = n_t * BN;
-      const int kb0 = ks * p.kb_per_split;
-      const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      const int kb0 = wu.kb0, kb1 = wu.kb1;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait<1>(&empty[s], ph ^ 1);
         if (lane == 0) {
@@ -228,9 +261,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int w = cluster_id; w < total; w += nclusters) {
-      const int tile = w / p.splits, ks = w - tile * p.splits;
-      const int kb0 = ks * p.kb_per_split;
-      const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      const WorkUnit wu = decode_unit<EPI>(p, w);
+      const int kb0 = wu.kb0, kb1 = wu.kb1;
       mbar_wait<2>(&tempty[acc], acc_ph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -284,9 +316,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     DropKey dk = {0u, 0u, 0u, 1.f};
     if constexpr (EPI & F_DROP) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
     for (int w = cluster_id; w < total; w += nclusters) {
-      const int tile = w / p.splits;
+      const WorkUnit wu = decode_unit<EPI>(p, w);
+      const int tile = wu.tile;
       const int n_t = tile / p.num_mp, m_t = (tile - n_t * p.num_mp) * 2 + (int)crank;
       const int m0 = m_t * C::BM, n0 = n_t * BN + half * (BN / 2);
+      // tail split: slices > 0 park their raw accumulators in the workspace, slice 0 adds them in
+      // slice order before its epilogue (fixed order: bit-reproducible)
+      bool tail_part = false, tail_own = false;
+      float* tail_blk = nullptr;  // this warp's 32 x (BN/2) block inside the partial tile of slice 1
+      constexpr size_t TAIL_TILE = (size_t)2 * C::BM * BN;  // floats per (tile, slice): both CTAs of the pair
+      if constexpr (EPI & F_TAIL) {
+        if (wu.nsl > 1) {
+          tail_part = wu.slice > 0;
+          tail_own = !tail_part;
+          const size_t tu = (size_t)(tile - p.tail_full);
+          tail_blk = p.tail_ws + (tu * (size_t)(p.tail_S - 1) + (size_t)(tail_part ? wu.slice - 1 : 0)) * TAIL_TILE +
+                     (size_t)crank * C::BM * BN + (size_t)(q * 32) * BN + half * (BN / 2);
+        }
+      }
       const int row_base = m0 + q * 32;
       const long long row0 = row_base + rs;
       // bias of the first chunk is fetched BEFORE waiting for the MMAs; later chunks prefetch
@@ -308,6 +355,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       load_bias(0, b4, bs);
       mbar_wait<4>(&tfull[acc], acc_ph);
       tc_fence_after();
+      if constexpr (EPI & F_TAIL) {
+        if (tail_own) {  // all partial slices of this tile have landed (16 epilogue warps each)
+          if (lane == 0) {
+            const unsigned int* flag = p.tail_flags + (tile - p.tail_full);
+            const unsigned int want = (unsigned int)(p.tail_S - 1) * 16u;
+            unsigned int v, spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+              if (++spins > (1u << 26)) {
+                printf("mmtg: GEMM tail-split wait timed out (tile %d, saw %u of %u)\n", tile, v, want);
+                __trap();
+              }
+            } while (v < want);
+          }
+          __syncwarp();
+        }
+      }
       float run_max = -INFINITY, run_sum = 0.f;
       bool released = false;
 #pragma unroll 1
@@ -332,7 +396,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int it = 0; it < 8; ++it) ok[it] = colok && (row_base + it * 4 + rs) < p.M;
           if constexpr (EPI & F_RES) {
-            if (p.residual) {
+            if (p.residual && !tail_part) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
                 res[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(p.residual + (row0 + it * 4) * p.ldr + col))
@@ -383,6 +447,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
         __syncwarp();
+        if constexpr (EPI & F_TAIL) {
+          if (tail_part) {  // raw accumulators -> workspace, 128 contiguous bytes per row
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rl = it * 4 + rs;
+              const float4 t = *reinterpret_cast<const float4*>(epi + rl * 32 + ((cg ^ (rl & 7)) << 2));
+              __stcg(reinterpret_cast<float4*>(tail_blk + (size_t)rl * BN + c * 32 + cg * 4), t);
+            }
+            b4 = b4n;
+            bs = bsn;
+            __syncwarp();
+            continue;
+          }
+        }
         if constexpr (!(EPI & F_SCALAR)) {
           // phase 2 (vector): 8 iterations of 4 rows x 32 columns; every global access is a full
           // 16-byte (fp32) / 8-byte (bf16) vector, 128 contiguous bytes per row.
@@ -391,8 +469,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + rs;
             const float4 t = *reinterpret_cast<const float4*>(epi + rl * 32 + ((cg ^ (rl & 7)) << 2));
-            v[it][0] = t.x + b4.x; v[it][1] = t.y + b4.y;
-            v[it][2] = t.z + b4.z; v[it][3] = t.w + b4.w;
+            v[it][0] = t.x; v[it][1] = t.y; v[it][2] = t.z; v[it][3] = t.w;
+          }
+          if constexpr (EPI & F_TAIL) {
+            if (tail_own) {
+              for (int sl = 0; sl + 1 < p.tail_S; ++sl) {
+                const float* src = tail_blk + (size_t)sl * TAIL_TILE + c * 32 + cg * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(it * 4 + rs) * BN));
+                  v[it][0] += t.x; v[it][1] += t.y; v[it][2] += t.z; v[it][3] += t.w;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            v[it][0] += b4.x; v[it][1] += b4.y; v[it][2] += b4.z; v[it][3] += b4.w;
           }
           bool act_done = false;
           if constexpr (EPI & F_OUT2) {
@@ -603,6 +696,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         bs = bsn;
         __syncwarp();
       }
+      if constexpr (EPI & F_TAIL) {
+        if (tail_part) {  // this warp's share of the partial tile is written: release + count
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence();
+            atomicAdd(p.tail_flags + (tile - p.tail_full), 1u);
+          }
+        } else if (tail_own) {  // the last of the pair's 16 owner warps re-arms the flags for the next launch
+          __syncwarp();
+          if (lane == 0) {
+            unsigned int* done = p.tail_flags + 128 + (tile - p.tail_full);
+            if (atomicAdd(done, 1u) == 15u) {
+              *done = 0u;
+              p.tail_flags[tile - p.tail_full] = 0u;
+            }
+          }
+        }
+      }
       if constexpr (EPI & F_LSE) {
         if (p.lse_partial) {
           // the two column halves of a 128/256-wide tile keep separate partial slots
@@ -721,6 +832,40 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
 
 void count_launch(int n = 1);
 
+// Tail-split workspace (partial accumulators + flags), one per (device, stream): GEMMs of one
+// stream are serialised, so they can share it; launches on different streams never do.
+struct TailWs {
+  float* ws;
+  unsigned int* flags;
+};
+constexpr size_t TAIL_WS_TILES = 80;                            // (tile, slice) partial tiles: <= clusters per grid
+constexpr size_t TAIL_WS_BYTES = TAIL_WS_TILES * 2 * 128 * 256 * 4;  // 256 x 256 fp32 per pair tile
+static bool tail_workspace(cudaStream_t st, TailWs* out) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, TailWs> map;
+  const unsigned long long key = ((unsigned long long)(uintptr_t)st << 6) ^ (unsigned long long)current_device_index();
+  std::lock_guard<std::mutex> g(mu);
+  auto it = map.find(key);
+  if (it != map.end()) {
+    *out = it->second;
+    return out->ws != nullptr;
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return false;  // no allocation inside a capture: this launch runs without the tail split
+  }
+  TailWs t{nullptr, nullptr};
+  if (cudaMalloc(&t.ws, TAIL_WS_BYTES) != cudaSuccess || cudaMalloc(&t.flags, 256 * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(t.flags, 0, 256 * sizeof(unsigned int)) != cudaSuccess) {
+    cudaGetLastError();
+    t.ws = nullptr;
+  }
+  map.emplace(key, t);
+  *out = t;
+  return t.ws != nullptr;
+}
+
 template <int BN, uint32_t EPI, bool TWO>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        cudaStream_t st) {
@@ -731,7 +876,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int total = p.num_mp * p.num_n * p.splits;  // work units of a CTA pair
+  const int total = (EPI & F_TAIL) ? p.tail_total : p.num_mp * p.num_n * p.splits;  // work units of a CTA pair
   // MMTG_GEMM_CTAS caps the persistent grid (data-parallel runs leave a few SMs to the NCCL
   // kernels: a persistent CTA pair that cannot become resident until an all-reduce kernel exits
   // delays its statically assigned tiles, and with them the whole GEMM)
@@ -859,6 +1004,41 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
     const char* e = getenv("MMTG_GEMM_2SM");
     return !(e && e[0] == '0');
   }();
+  // Tail split: with U tile pairs on C clusters the last, partial round leaves C - U % C clusters
+  // idle for a whole tile time (the N = 768 GEMMs of the decoder: 90 pairs on 74 clusters = two
+  // rounds for 1.22 rounds of work). The T = U % C tiles of that round are cut into S = C / T
+  // k-slices, one per cluster; slice 0 adds the other slices' fp32 partials (parked in an L2-resident
+  // workspace) in slice order and runs the epilogue. Deterministic, no atomics on the output.
+  // MEASURED (round 2, B200): correct and bit-reproducible, but SLOWER than the plain two rounds -
+  // 7552 x 768 x 3072 46.0 us vs 43.8 us, train step 8.69 ms vs 8.25 ms: slice 0 reads the three
+  // partial tiles (384 KB per CTA) as 12 dependent L2 round trips per warp, which costs more than
+  // the 0.75 tile time the split saves. Opt-in (MMTG_GEMM_TAIL=1) until the fix-up is pipelined.
+  static const bool tail_on = []() {
+    const char* e = getenv("MMTG_GEMM_TAIL");
+    return e && e[0] == '1';
+  }();
+  p.tail_full = p.tail_S = p.tail_kbs = p.tail_total = 0;
+  p.tail_ws = nullptr;
+  p.tail_flags = nullptr;
+  if (tail_on && two_sm && BN == 256 && !p.atomic && p.splits == 1 && p.vec4 && p.grid_mode == 0 &&
+      (need & ~(uint32_t)(F_RES | F_DROP)) == 0 && !getenv("MMTG_GEMM_CTAS")) {
+    const int U = p.num_mp * p.num_n, Cn = num_sms() / 2;
+    const int T = U % Cn;
+    const int S = T > 0 ? Cn / T : 0;
+    if (U > Cn && S >= 2 && p.num_kb >= 2 * S && (size_t)T * (S - 1) <= TAIL_WS_TILES && T <= 128) {
+      TailWs tw;
+      if (tail_workspace(st, &tw)) {
+        p.tail_full = U - T;
+        p.tail_S = S;
+        p.tail_kbs = cdiv(p.num_kb, S);
+        p.tail_S = cdiv(p.num_kb, p.tail_kbs);  // (slices that would be empty are dropped)
+        p.tail_total = p.tail_full + T * p.tail_S;
+        p.tail_ws = tw.ws;
+        p.tail_flags = tw.flags;
+        need |= F_TAIL;
+      }
+    }
+  }
 #define MMTG_TRY_EPI(MASK)                                                        \
   if ((need & ~(uint32_t)(MASK)) == 0) {                                          \
     if (two_sm) {                                                                 \
@@ -867,6 +1047,10 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
     }                                                                             \
     if (BN == 256) return launch_gemm<256, (MASK), false>(tmA, tmB, p, st);       \
     return launch_gemm<128, (MASK), false>(tmA, tmB, p, st);                      \
+  }
+  if (need & F_TAIL) {
+    if ((need & ~(uint32_t)F_TAIL) == 0) return launch_gemm<256, F_TAIL, true>(tmA, tmB, p, st);
+    return launch_gemm<256, F_TAIL | F_RES | F_DROP, true>(tmA, tmB, p, st);
   }
   MMTG_TRY_EPI(0u)
   MMTG_TRY_EPI(F_ACT | F_OUT2)

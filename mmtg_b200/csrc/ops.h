@@ -18,6 +18,9 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, bf16* y
 int layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd,
                   const float* gamma, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
                   bf16* dx16, float* dx_colsum, int M, int E, cudaStream_t st, const DropSpec* drop = nullptr);
+// dgamma / dbeta / column sums of dx16 of a LayerNorm backward whose chain part ran without them
+int ln_param_grads(const bf16* dy, const float* x, const float* mean, const float* rstd, const bf16* dx16,
+                   float* dgamma, float* dbeta, float* dx_colsum, int M, int E, cudaStream_t st);
 int cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
 int colsum(const void* x, int x_bf16, long long ld, bf16* copy16, long long ldc, float* out, int M,
            int N, cudaStream_t st);

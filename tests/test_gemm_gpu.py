@@ -148,3 +148,33 @@ def test_skinny_decode_gemm(cuda, M, N, K, w_kn):
         ops.gemm(x, Ws, out, M=M, N=N, K=K, b_mn_major=w_kn, bias=bias, rowtab0=tab0, rowidx0=i0, rowtab1=tab1,
                  rowidx1=i1, skinny=True)
         assert (out - (base + tab0[i0.long()] + tab1[i1.long()])).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("K,out_dtype", [(768, torch.bfloat16), (3072, torch.float32), (2304, torch.bfloat16)])
+def test_gemm_tail_split(cuda, K, out_dtype):
+    """The decoder's N = 768 GEMMs at the bench batch (90 tile pairs on 74 clusters): the 16 tiles of
+    the partial last round are cut into 4 k-slices whose fp32 partials slice 0 adds in a fixed order
+    (csrc/gemm_sm100.cu, F_TAIL). Checked against the fp32 reference, with the residual epilogue,
+    and for run-to-run bit-equality (there are no atomics on the output). The split is opt-in
+    (MMTG_GEMM_TAIL=1, measured slower than two plain rounds); without it the test covers the same
+    shapes on the default path."""
+    from mmtg_b200 import ops
+    M, N = 7552, 768
+    g = torch.Generator(device=cuda).manual_seed(K)
+    A = torch.randn(M, K, generator=g, device=cuda).to(torch.bfloat16)
+    B = (torch.randn(N, K, generator=g, device=cuda) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device=cuda)
+    res = torch.randn(M, N, generator=g, device=cuda)
+    ref = A.float() @ B.float().t() + bias + res
+    outs = []
+    for _ in range(3):
+        out = torch.full((M, N), float("nan"), device=cuda, dtype=out_dtype)
+        ops.gemm(A, B, out, M=M, N=N, K=K, bias=bias, residual=res, block_n=256)
+        torch.cuda.synchronize()
+        outs.append(out)
+    tol = 2e-3 * math.sqrt(K / 64)
+    if out_dtype == torch.float32:
+        assert (outs[0] - ref).abs().max().item() <= tol
+    else:
+        assert torch.allclose(outs[0].float(), ref, atol=tol, rtol=8e-3)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
