@@ -61,6 +61,7 @@ struct GemmParams {
   uint32_t drop_site;
   float drop_p;
   int grid_mode;
+  int clc;  // 1: work units come from cluster launch control (see TileSched), 0: static round-robin
   // tail split (F_TAIL): work units [0, tail_full) are whole tiles; each tile >= tail_full is cut into
   // tail_S k-slices of tail_kbs k-blocks (slice 0 owns the epilogue and adds the others' partials)
   int tail_full, tail_S, tail_kbs, tail_total;
@@ -79,14 +80,15 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (232448 - 8 * 32 * 32 * 4 - 256 - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (232448 - 8 * 32 * 32 * 4 - 512 - 1024) / STAGE_BYTES;
   static constexpr int EPI_PITCH = 32;  // floats; XOR-swizzled 16-B chunks, no padding
   static constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH;
   static constexpr int EPI_BYTES = 8 * EPI_WARP_FLOATS * 4;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;  // ring / accumulator barriers [0,192), TMEM slot 192, scheduler 256..
+  static_assert((2 * STAGES + 4) * 8 <= 192, "barrier block overflows into the TMEM slot");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
-  static constexpr int THREADS = 320;
+  static constexpr int TMEM_COLS = BN == 192 ? 512 : 2 * BN;  // allocations are powers of two (192: 384 used)
+  static constexpr int THREADS = 352;  // 10 working warps + the tile-scheduler warp
 };
 
 // epilogue feature bits (compile-time mask EPI)
@@ -123,8 +125,86 @@ __device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int w) {
   return u;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Work distribution. Static mode: cluster c takes units c, c + #clusters, ... (a CTA pair that
+// cannot become resident - its SMs are held by a kernel of another stream: a weight-gradient GEMM
+// of the side stream, an NCCL all-reduce - keeps its units hostage until it starts). Dynamic mode
+// (sm_100 cluster launch control): the grid has ONE cluster per work unit; a running cluster,
+// when it finishes a unit, cancels a cluster that has not been launched yet and takes over its
+// unit. Whatever SMs are available at any moment share the remaining work.
+// The scheduler warp of the pair's CTA 0 issues `clusterlaunchcontrol.try_cancel` (multicast: the
+// 16-byte response lands in both CTAs' shared memory and completes 16 bytes on both CTAs'
+// `clc_full` barriers); the producer, MMA and epilogue warps of both CTAs read it and release
+// the slot on CTA 0's `clc_empty` (20 arrivals).
+// ---------------------------------------------------------------------------------------------
+constexpr int CLC_STAGES = 3;
+constexpr int CLC_CONSUMERS = 20;  // (producer + MMA + 8 epilogue warps) x 2 CTAs
+
+__device__ __forceinline__ void clc_try_cancel(void* resp, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(smem_u32(resp)), "r"(smem_u32(bar))
+      : "memory");
+}
+// -> first CTA id (x) of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_read(const void* resp) {
+  uint32_t x, y, z, valid;
+  asm volatile(
+      "{\n"
+      ".reg .pred p1;\n"
+      ".reg .b128 r;\n"
+      "ld.shared.b128 r, [%4];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n"
+      "selp.u32 %3, 1, 0, p1;\n"
+      "mov.u32 %0, 0;\n"
+      "mov.u32 %1, 0;\n"
+      "mov.u32 %2, 0;\n"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n"
+      "}\n"
+      : "=r"(x), "=r"(y), "=r"(z), "=r"(valid)
+      : "r"(smem_u32(resp))
+      : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot is rewritten through the async proxy
+  return valid ? (int)x : -1;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint64_t* bar, uint32_t rank, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank), "r"(bytes)
+      : "memory");
+}
+// per-warp cursor over the work units of this cluster
+struct TileSched {
+  int w;
+  uint32_t stage, phase;
+  int step, total, clc;
+  uint64_t *full, *empty;
+  const uint8_t* resp;
+  __device__ __forceinline__ bool valid() const { return w >= 0 && w < total; }
+  // whole warp calls; lane 0 releases the slot
+  __device__ __forceinline__ void next() {
+    if (!clc) {
+      w += step;
+      return;
+    }
+    mbar_wait<7>(&full[stage], phase);
+    const int cta = clc_read(resp + stage * 16);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(&empty[stage], 0);
+    if (++stage == CLC_STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+    w = cta < 0 ? -1 : (cta >> 1);
+  }
+};
+
 template <int BN, uint32_t EPI, bool TWO>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using C = GemmCfg<BN, TWO>;
@@ -136,7 +216,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint8_t* bar_blk = smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES;
+  uint32_t* tmem_slot = (uint32_t*)(bar_blk + 192);
+  uint64_t* clc_full = (uint64_t*)(bar_blk + 256);  // [CLC_STAGES]
+  uint64_t* clc_empty = (uint64_t*)(bar_blk + 288);
+  uint8_t* clc_resp = bar_blk + 320;                // [CLC_STAGES][16]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,6 +239,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], TWO ? 16 : 8);  // 2-SM: both CTAs' epilogue warps release the leader
+    }
+    for (int a = 0; a < CLC_STAGES; ++a) {
+      mbar_init(&clc_full[a], 1);
+      mbar_init(&clc_empty[a], CLC_CONSUMERS);
     }
     fence_barrier_init();
   }
@@ -185,12 +273,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int cluster_id = blockIdx.x >> 1;
   const int nclusters = gridDim.x >> 1;
   const int total = (EPI & F_TAIL) ? p.tail_total : p.num_mp * p.num_n * p.splits;  // work units of a PAIR
+  TileSched ts{cluster_id, 0u, 0u, nclusters, total, p.clc, clc_full, clc_empty, clc_resp};
 
-  if (warp == 0) {
+  if (warp == 10) {
+    // ===================== tile scheduler (dynamic mode, CTA 0 of the pair) =====================
+    if (p.clc && crank == 0 && lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      while (true) {
+        mbar_wait<8>(&clc_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx_cluster(&clc_full[stage], 0, 16);
+        mbar_arrive_expect_tx_cluster(&clc_full[stage], 1, 16);
+        clc_try_cancel(clc_resp + stage * 16, &clc_full[stage]);
+        mbar_wait<9>(&clc_full[stage], phase);
+        const int cta = clc_read(clc_resp + stage * 16);
+        if (++stage == CLC_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (cta < 0) break;  // nothing left to cancel: further requests are not allowed
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     int s = 0;
     uint32_t ph = 0;
-    for (int w = cluster_id; w < total; w += nclusters) {
+    for (; ts.valid(); ts.next()) {
+      const int w = ts.w;
       const WorkUnit wu = decode_unit<EPI>(p, w);
       const int tile = wu.tile;
       const int n_t = tile / p.num_mp, m_t = (tile - n_t * p.num_mp) * 2 + (int)crank;
@@ -248,7 +356,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
       }
     }
-  } else if (warp == 1 && !(TWO && crank != 0)) {
+  } else if (warp == 1 && TWO && crank != 0) {
+    // the peer's MMA warp has no work in 2-SM mode but still consumes the schedule (releases its slots)
+    for (; ts.valid(); ts.next()) {
+    }
+  } else if (warp == 1) {
     // ===================== MMA issuer (2-SM mode: leader CTA only) =====================
     const uint32_t idesc = umma_idesc_bf16(TWO ? 2 * C::BM : C::BM, BN, p.a_mn, p.b_mn);
     // K-major SW128: 8-row atoms 1024 B apart (SBO), UMMA_K=16 advances 32 B inside the row.
@@ -260,8 +372,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     uint32_t ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int w = cluster_id; w < total; w += nclusters) {
-      const WorkUnit wu = decode_unit<EPI>(p, w);
+    for (; ts.valid(); ts.next()) {
+      const WorkUnit wu = decode_unit<EPI>(p, ts.w);
       const int kb0 = wu.kb0, kb1 = wu.kb1;
       mbar_wait<2>(&tempty[acc], acc_ph ^ 1);
       tc_fence_after();
@@ -299,7 +411,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         acc_ph ^= 1;
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < 10) {
     // ===================== epilogue warps (2..9) =====================
     // Two warps per TMEM lane quadrant: warps 2..5 own the left half of the tile's columns,
     // warps 6..9 the right half (a warp may only touch lanes 32*(warp%4) .. +31).
@@ -315,8 +427,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     uint32_t acc_ph = 0;
     DropKey dk = {0u, 0u, 0u, 1.f};
     if constexpr (EPI & F_DROP) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
-    for (int w = cluster_id; w < total; w += nclusters) {
-      const WorkUnit wu = decode_unit<EPI>(p, w);
+    for (; ts.valid(); ts.next()) {
+      const WorkUnit wu = decode_unit<EPI>(p, ts.w);
       const int tile = wu.tile;
       const int n_t = tile / p.num_mp, m_t = (tile - n_t * p.num_mp) * 2 + (int)crank;
       const int m0 = m_t * C::BM, n0 = n_t * BN + half * (BN / 2);
@@ -888,6 +1000,17 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   int max_clusters = num_sms() / 2;
   if (cta_cap && cta_cap / 2 < max_clusters) max_clusters = cta_cap / 2;
   if (p.grid_mode == 1) max_clusters = total;  // one work unit per CTA pair
+  // dynamic scheduling (cluster launch control): one cluster per work unit in the grid; the
+  // resident clusters cancel and absorb the ones not launched yet (see TileSched)
+  // MEASURED (round 2): correct, but not faster - train step 8.50 ms vs 8.35 ms static on 1 GPU,
+  // 8.83 vs 8.73 ms on 2 GPUs (NCCL all-reduce kernels competing for SMs). Opt-in: MMTG_GEMM_CLC=1.
+  static const bool clc_on = []() {
+    const char* e = getenv("MMTG_GEMM_CLC");
+    return e && e[0] == '1';
+  }();
+  GemmParams pl = p;
+  pl.clc = (clc_on && p.grid_mode == 0 && !cta_cap && !(EPI & F_TAIL)) ? 1 : 0;
+  if (pl.clc) max_clusters = total;
   const int grid = 2 * (total < max_clusters ? total : max_clusters);
   ProfScope prof(0, 2.0 * p.M * p.N * p.K,
                  2.0 * ((double)p.M * p.K + (double)p.N * p.K) + (p.out_bf16 ? 2.0 : 4.0) * p.M * p.N, st);
@@ -910,7 +1033,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 2 : 1;
-  MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, TWO>, tmA, tmB, p));
+  MMTG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, TWO>, tmA, tmB, pl));
   MMTG_LAUNCH_OK();
   count_launch();
   return 0;
@@ -931,7 +1054,9 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
     BN = (a->N >= 256 && t256 >= 96) ? 256 : 128;
     if (a->N <= 128) BN = 128;
   }
-  MMTG_CHECK_ARG(BN == 128 || BN == 256, "block_n must be 0, 128 or 256");
+  MMTG_CHECK_ARG(BN == 128 || BN == 192 || BN == 256, "block_n must be 0, 128, 192 or 256");
+  const bool want192 = BN == 192;
+  if (want192) BN = 256;  // decided below, once the epilogue features are known
   const bool atomic = a->accumulate != 0 || a->split_k > 1;
   MMTG_CHECK_ARG(!(atomic && a->out_dtype != MMTG_F32), "accumulate/split_k need an fp32 out");
   MMTG_CHECK_ARG(!(a->rowtab0 && !a->rowidx0 && a->rowmod0 <= 0), "rowtab0 needs rowidx0 or rowmod0");
@@ -977,6 +1102,37 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
                    "out2/dgelu_src/rowtab epilogues need N %% 4 == 0 and 16-byte aligned operands");
   }
 
+  static const bool two_sm = []() {  // MMTG_GEMM_2SM=0 selects the 1-SM (multicast) kernel
+    const char* e = getenv("MMTG_GEMM_2SM");
+    return !(e && e[0] == '0');
+  }();
+  {
+    // 192-wide tiles for plain K-major-B GEMMs whose tile count quantises badly on the 74 CTA pairs:
+    // the decoder's N = 768 dgrads are 90 pairs of 256 columns (two rounds for 1.22 rounds of work)
+    // or 120 pairs of 192 columns (two rounds of 3/4 the size).
+    // MEASURED (round 2): no gain - 7552 x 768 x {768, 2304, 3072}: 21.4 / 35.8 / 43.9 us against
+    // 20.5 / 35.8 / 45.1 us with 256-wide tiles (cuBLAS: 17.4 / 27.6 / 33.6 us, stream-K): the
+    // narrower pair tile needs 28 KB of operands per 384 MMA cycles (73 B/clk/SM, above the
+    // ~64 B/clk the L2 delivers), so each of the smaller tiles runs slower. Explicit block_n = 192
+    // or MMTG_GEMM_BN192=1 select it.
+    static const bool bn192_on = []() {
+      const char* e = getenv("MMTG_GEMM_BN192");
+      return e && e[0] == '1';
+    }();
+    const bool plain = !p.out2 && p.act == MMTG_ACT_NONE && !p.dgelu_src && !p.residual && !p.rowtab0 && !p.rowtab1 &&
+                       !p.colsum && !p.atomic && !p.lse_partial && p.vec4 && !(a->drop_seed && a->drop_p > 0.f) &&
+                       p.splits == 1 && !p.b_mn && two_sm;
+    MMTG_CHECK_ARG(!want192 || plain, "block_n 192 serves plain (no epilogue features) GEMMs with a K-major B operand");
+    if (plain && BN == 256 && (want192 || (bn192_on && a->block_n == 0))) {
+      const int Cn = num_sms() / 2;
+      const long long c256 = (long long)cdiv(p.num_mp * cdiv(a->N, 256), Cn) * 256;
+      const long long c192 = (long long)cdiv(p.num_mp * cdiv(a->N, 192), Cn) * 192;
+      if (want192 || c192 < c256) {
+        BN = 192;
+        p.num_n = cdiv(a->N, 192);
+      }
+    }
+  }
   CUtensorMap tmA, tmB;
   if (!p.a_mn) MMTG_TRY(make_tmap_bf16_2d(&tmA, a->A, a->K, a->M, a->lda, 64, 128));
   else         MMTG_TRY(make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, 64, 64));
@@ -1000,10 +1156,6 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
                    "dropout epilogue: needs p < 1, N %% 4 == 0, aligned operands, and a residual or row-table epilogue");
     need |= F_DROP;
   }
-  static const bool two_sm = []() {  // MMTG_GEMM_2SM=0 selects the 1-SM (multicast) kernel
-    const char* e = getenv("MMTG_GEMM_2SM");
-    return !(e && e[0] == '0');
-  }();
   // Tail split: with U tile pairs on C clusters the last, partial round leaves C - U % C clusters
   // idle for a whole tile time (the N = 768 GEMMs of the decoder: 90 pairs on 74 clusters = two
   // rounds for 1.22 rounds of work). The T = U % C tiles of that round are cut into S = C / T
@@ -1048,6 +1200,7 @@ extern "C" int mmtg_gemm_bf16(const mmtg_gemm_args* a, void* stream) {
     if (BN == 256) return launch_gemm<256, (MASK), false>(tmA, tmB, p, st);       \
     return launch_gemm<128, (MASK), false>(tmA, tmB, p, st);                      \
   }
+  if (BN == 192) return launch_gemm<192, 0u, true>(tmA, tmB, p, st);
   if (need & F_TAIL) {
     if ((need & ~(uint32_t)F_TAIL) == 0) return launch_gemm<256, F_TAIL, true>(tmA, tmB, p, st);
     return launch_gemm<256, F_TAIL | F_RES | F_DROP, true>(tmA, tmB, p, st);

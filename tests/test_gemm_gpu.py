@@ -178,3 +178,26 @@ def test_gemm_tail_split(cuda, K, out_dtype):
     else:
         assert torch.allclose(outs[0].float(), ref, atol=tol, rtol=8e-3)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("M,N,K", [(7552, 768, 768), (7552, 768, 3072), (300, 520, 200), (472, 2304, 768)])
+@pytest.mark.parametrize("a_mn", [False, True])
+def test_gemm_bn192(cuda, M, N, K, a_mn):
+    """192-column tile pairs (plain K-major-B GEMMs; the engine's N = 768 dgrads pick them by
+    themselves at M = 7552: 120 pairs on 74 CTA pairs instead of 90)."""
+    from mmtg_b200 import ops
+    if a_mn and M % 8:
+        pytest.skip("pitch not TMA-aligned for this layout")
+    g = torch.Generator(device=cuda).manual_seed(M + N + K)
+    A, As = _mk(M, K, a_mn, g, cuda)
+    B, Bs = _mk(N, K, False, g, cuda)
+    ref = A.float() @ B.float().t()
+    tol = 2e-3 * math.sqrt(max(K, 64) / 64)
+    for dt in (torch.float32, torch.bfloat16):
+        out = torch.full((M, N), float("nan"), device=cuda, dtype=dt)
+        ops.gemm(As, Bs, out, M=M, N=N, K=K, a_mn_major=a_mn, block_n=192)
+        torch.cuda.synchronize()
+        if dt == torch.float32:
+            assert (out - ref).abs().max().item() <= tol
+        else:
+            assert torch.allclose(out.float(), ref, atol=tol, rtol=8e-3)
