@@ -689,6 +689,41 @@ def main():
     except Exception:
         pass
 
+    # reported context for the tensor roofline: the dominant contraction (M x 3072 x 768, plain bf16
+    # output) launched alone with a cold L2 - this library next to cuBLAS (torch.matmul). The burst
+    # peak in MEASURED_PEAKS.json is cuBLAS at 8192^3; at K = 768 a tile is 12 k-blocks long and
+    # neither kernel gets close to it, so this is the like-for-like reference of `frac`.
+    same_shape = None
+    if world == 1:
+        try:
+            from mmtg_b200 import ops as _ops
+            Mg = B * L
+            ga = torch.randn(Mg, 768, device=dev).to(torch.bfloat16)
+            gw = (torch.randn(3072, 768, device=dev) * 0.05).to(torch.bfloat16)
+            go = torch.empty(Mg, 3072, device=dev, dtype=torch.bfloat16)
+
+            def _med(fn, n=7):
+                for _ in range(3):
+                    fn()
+                ts = []
+                for _ in range(n):
+                    flush.zero_()
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    fn()
+                    a1.record()
+                    torch.cuda.synchronize()
+                    ts.append(a0.elapsed_time(a1))
+                return sorted(ts)[len(ts) // 2]
+            t_own = _med(lambda: _ops.gemm(ga, gw, go, M=Mg, N=3072, K=768))
+            t_lib = _med(lambda: torch.matmul(ga, gw.t(), out=go))
+            same_shape = {"shape": [Mg, 3072, 768], "this_library_us": 1e3 * t_own, "this_library_tflops": dom_flops / t_own / 1e9,
+                          "cublas_us": 1e3 * t_lib, "cublas_tflops": dom_flops / t_lib / 1e9,
+                          "how": "one launch at a time, 256 MB L2 flush before each, CUDA events, median of 7; cuBLAS = torch.matmul (bf16)"}
+            del ga, gw, go
+        except Exception as exc:  # a reported baseline must never take the bench down
+            same_shape = {"error": repr(exc)}
+
     gb = torch.tensor([float(B)], device=dev)
     if world > 1:
         dist.all_reduce(gb, op=dist.ReduceOp.SUM)  # ragged per-rank batches after a stage-1/2 filter
@@ -718,7 +753,8 @@ def main():
                          "peak_source": f"MEASURED_PEAKS.json {peak_name} ({pk_src})",
                          "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
                          "all_gemm_launches_tflops": all_gemm_tflops,
-                         "step_model_flops_frac": (value / world) * gflop_per_sample / 1e3 / peak},
+                         "step_model_flops_frac": (value / world) * gflop_per_sample / 1e3 / peak,
+                         "same_shape_alone": same_shape},
             "breakdown": classes,
         }
         if parity is not None:

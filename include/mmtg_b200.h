@@ -129,6 +129,14 @@ int mmtg_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const float* x, const
                        const float* rstd, const float* gamma, float* dx, int32_t accumulate_dx,
                        float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, int32_t M,
                        int32_t E, void* stream);
+/* The parameter-gradient half of the LayerNorm backward when mmtg_layernorm_bwd ran WITHOUT
+ * dgamma / dbeta / dx_colsum (E = 768, bf16 dy: the engine's chain / side-stream split):
+ * dgamma[E] += sum_rows dy * xhat, dbeta[E] += sum_rows dy, dx_colsum[E] += column sums of the bf16
+ * dx copy (the bias gradient autograd computes for the Linear/Conv1D feeding this LayerNorm's
+ * input; HF modeling_gpt2.py GPT2Block residual adds). E % 128 == 0. */
+int mmtg_ln_param_grads(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                        const void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int32_t M,
+                        int32_t E, void* stream);
 int mmtg_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* bias gradients: out[N] += column sums of x[M,N]; optional bf16 copy of an fp32 x */
 int mmtg_colsum(const void* x, int32_t x_is_bf16, int64_t ld, void* copy_bf16, int64_t ldc,
@@ -151,6 +159,9 @@ int mmtg_attn_bwd(const void* qkv, const int32_t* key_mask, const void* out, con
  * (forward: any L; backward: L <= 256, whole head per CTA) */
 /* debugging aid: per-(block, warp) progress codes written to host-mapped memory (null = off) */
 void mmtg_attn_set_trace(int32_t* host_mapped);
+/* debugging aid: CTA 0 of the tcgen05 attention backward stamps %globaltimer (ns) at its stage
+ * boundaries into dev_buf (>= 64 entries; scripts/attn_bwd_trace.py); NULL disables */
+void mmtg_attn_set_clk(uint64_t* dev_buf);
 int mmtg_attn_fwd_ex(const void* qkv, const int32_t* key_mask, void* out, float* lse, int32_t B,
                      int32_t L, int32_t n_head, int32_t impl, void* stream);
 int mmtg_attn_bwd_ex(const void* qkv, const int32_t* key_mask, const void* out, const void* dout,

@@ -622,6 +622,14 @@ extern "C" int mmtg_layernorm_fwd(const float* x, const float* gamma, const floa
   MMTG_CHECK_ARG(x && gamma && beta && (y_bf16 || y_f32) && M > 0, "bad layernorm args");
   return layernorm_fwd(x, gamma, beta, (bf16*)y_bf16, y_f32, mean, rstd, M, E, eps, (cudaStream_t)stream);
 }
+extern "C" int mmtg_ln_param_grads(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                                   const void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int32_t M,
+                                   int32_t E, void* stream) {
+  MMTG_CHECK_ARG(dy_bf16 && x && mean && rstd && M > 0 && (dgamma || dbeta || dx_colsum), "bad ln_param_grads args");
+  MMTG_CHECK_ARG(!dx_colsum || dx_bf16, "dx_colsum needs the bf16 dx copy");
+  return ln_param_grads((const bf16*)dy_bf16, x, mean, rstd, (const bf16*)dx_bf16, dgamma, dbeta, dx_colsum, M, E,
+                        (cudaStream_t)stream);
+}
 extern "C" int mmtg_layernorm_bwd(const void* dy, int32_t dy_is_bf16, const float* x, const float* mean,
                                   const float* rstd, const float* gamma, float* dx,
                                   int32_t accumulate_dx, float* dgamma, float* dbeta, void* dx_bf16,

@@ -94,6 +94,12 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx16=
                                              _p(dx16), _p(dx_colsum), M, E, _st()), "mmtg_layernorm_bwd")
 
 
+def ln_param_grads(dy16, x, mean, rstd, dx16, dgamma, dbeta, dx_colsum):
+    M, E = x.shape
+    _lib.check(_lib.lib().mmtg_ln_param_grads(_p(dy16), _p(x), _p(mean), _p(rstd), _p(dx16), _p(dgamma), _p(dbeta),
+                                              _p(dx_colsum), M, E, _st()), "mmtg_ln_param_grads")
+
+
 def colsum(x, out, copy16=None):
     M, N = x.shape
     _lib.check(_lib.lib().mmtg_colsum(_p(x), int(x.dtype == torch.bfloat16), C.c_int64(x.stride(0)), _p(copy16),

@@ -10,21 +10,39 @@ filter rows by rating, src/train.py:178-183): build `GradSync(average=False)` an
 rank's loss gradient by `ragged_batch_scale(B_local)` = B_local / B_global
 (`MMTG.fused_train_step(..., grad_scale=...)`), so the SUM all-reduce reproduces the
 single-process gradient of the concatenated batch.
+
+Wire format. fp32 by default (N-rank gradients equal the single-rank ones to 4e-7,
+tests/ddp_worker.py). `GradSync(grad_dtype=torch.bfloat16)` / MMTG_DDP_GRAD_DTYPE=bf16 send each
+bucket as bf16 (cast on the communication stream, all-reduce of half the bytes, cast back into the
+fp32 gradient buffer; 2^-9 relative rounding per element and rank, measured 2.7e-3 worst tensor).
+MEASURED (round 2, B200, 32 samples per GPU): 8 GPUs 9.10 ms (bf16) vs 9.20 ms (fp32) per step,
+2 GPUs 8.89 ms vs 8.76 ms - the two extra cast passes over the gradient buffer (1.3 GB of HBM
+traffic per step) cost about what the shorter collective saves, so it stays opt-in. Also
+measured at 8 GPUs: capping NCCL at 16 / 8 channels lengthens the step to 9.80 / 11.64 ms (the
+collective's duration, not the SMs it occupies, is what is exposed), and dynamic GEMM tile
+scheduling (MMTG_GEMM_CLC=1) does not shorten it (9.32 vs 9.25 ms).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, process_group=None, average=True):
+    def __init__(self, process_group=None, average=True, grad_dtype=None):
         self.group = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._cuda = torch.cuda.is_available()
         self.comm_stream = torch.cuda.Stream() if self._cuda else None
         self.bytes_reduced = 0
+        if grad_dtype is None:
+            grad_dtype = torch.float32 if os.environ.get("MMTG_DDP_GRAD_DTYPE", "fp32").lower() in ("fp32", "float32") \
+                else torch.bfloat16
+        self.grad_dtype = grad_dtype
+        self._wire = None  # bf16 staging buffer, same offsets as the flat gradient buffer
 
     def _reduce(self, t):
         if self.world == 1 or t.numel() == 0:
@@ -33,16 +51,30 @@ class GradSync:
         if t.is_cuda:
             ev = torch.cuda.Event()
             ev.record()
+            op = dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
-                if self.average:
-                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+                if self.grad_dtype == torch.float32 or t.dtype != torch.float32:
+                    dist.all_reduce(t, op=op, group=self.group)
                 else:
-                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                    w = self._wire_view(t)
+                    self.bytes_reduced -= t.numel() * (t.element_size() - w.element_size())
+                    w.copy_(t)  # fp32 -> bf16 on the communication stream
+                    dist.all_reduce(w, op=op, group=self.group)
+                    t.copy_(w)
         else:  # gloo (CPU tests of the bucketing logic): no AVG
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             if self.average:
                 t.div_(self.world)
+
+    def _wire_view(self, t):
+        """bf16 staging slice for the gradient slice `t` (one buffer, allocated once: the caching
+        allocator must not hand out memory that a CUDA-graph pool owns)."""
+        n = t.untyped_storage().nbytes() // t.element_size()
+        if self._wire is None or self._wire.numel() != n or self._wire.device != t.device:
+            self._wire = torch.empty(n, dtype=self.grad_dtype, device=t.device)
+        o = t.storage_offset()
+        return self._wire[o:o + t.numel()]
 
     def after_stage(self, model, stage, nstage):
         G = model._flat[2]

@@ -1,0 +1,12 @@
+#!/bin/bash
+# 8-GPU A/B: static round-robin GEMM tiles vs cluster-launch-control dynamic scheduling under NCCL contention
+for c in 0 1; do
+  MMTG_GEMM_CLC=$c timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus 8 --steps 15 --warmup 5 --no-decode --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l)
+        print('clc=$c', d['n_gpus'], round(d['value'], 1), round(d['ms_per_step'], 3), d['roofline']['avg_launch_us'], {k: round(v['ms_per_step'], 2) for k, v in d['breakdown'].items()})
+" | tee -a gpurun_out/r2_n8_clc_ab.log
+done

@@ -73,9 +73,9 @@ def main():
     ref1 = build()
     t_ref1, _, _ = ref1.fused_train_step(take(idx1), 1, 0.2)
 
-    # ---------------- equal shards, AVG all-reduce, eager stage loop ----------------
+    # ---------------- equal shards, AVG all-reduce, eager stage loop (fp32 on the wire) ----------------
     model = build()
-    model.grad_sync = GradSync(average=True)
+    model.grad_sync = GradSync(average=True, grad_dtype=torch.float32)
     mine = torch.arange(rank * per, (rank + 1) * per)
     model.fused_train_step(take(mine), 3, 0.2)
     torch.cuda.synchronize()
@@ -90,9 +90,19 @@ def main():
     e, n = rel_errors(model, ref3)
     out["equal_graph"] = {"worst_rel": e, "param": n, "bytes_reduced": model.grad_sync.bytes_reduced}
     ok &= e <= 3e-3
+    # ---------------- opt-in wire format (bf16 buckets): half the NVLink bytes, 2^-9 rounding ----------------
+    model3 = build()
+    model3.grad_sync = GradSync(average=True, grad_dtype=torch.bfloat16)
+    model3.fused_train_step(take(mine), 3, 0.2)
+    torch.cuda.synchronize()
+    e, n = rel_errors(model3, ref3)
+    out["equal_bf16_wire"] = {"worst_rel": e, "param": n, "wire": str(model3.grad_sync.grad_dtype),
+                              "bytes_reduced": model3.grad_sync.bytes_reduced}
+    ok &= e <= 1e-2 and model3.grad_sync.grad_dtype == torch.bfloat16
+    del model3
     # ---------------- ragged shards: stage-1 filter per rank, SUM all-reduce ----------------
     model2 = build()
-    model2.grad_sync = GradSync(average=False)
+    model2.grad_sync = GradSync(average=False, grad_dtype=torch.float32)
     local_rows = mine[stage_row_indices(full["rating"][mine], 1)]
     out["ragged_rows"] = int(len(local_rows))
     scale = ragged_batch_scale(len(local_rows), device=dev)

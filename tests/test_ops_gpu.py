@@ -7,6 +7,36 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("M", [7552, 473])
+def test_layernorm_bwd_split(cuda, M):
+    """The engine's split of the decoder LayerNorm backward: row kernel on the chain (dx += ...,
+    bf16 copy; no parameter gradients requested) + ln_param_grads on the side stream, against
+    autograd of torch.nn.functional.layer_norm."""
+    from mmtg_b200 import ops
+    E = 768
+    g = torch.Generator(device=cuda).manual_seed(M)
+    x = torch.randn(M, E, generator=g, device=cuda) * 2 + 0.3
+    gamma = 1 + 0.1 * torch.randn(E, generator=g, device=cuda)
+    beta = 0.1 * torch.randn(E, generator=g, device=cuda)
+    _y16, _y32, mean, rstd = ops.layernorm_fwd(x, gamma, beta, want_f32=True)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (E,), gr, br, 1e-5)
+    dy = (torch.randn(M, E, generator=g, device=cuda) * 0.1).to(torch.bfloat16)
+    ref.backward(dy.float())
+    base = torch.randn(M, E, generator=g, device=cuda)
+    dx = base.clone()
+    dx16 = torch.empty(M, E, device=cuda, dtype=torch.bfloat16)
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, True, None, None, dx16, None)
+    assert torch.allclose(dx - base, xr.grad, atol=2e-5, rtol=1e-4)
+    assert torch.equal(dx16, dx.to(torch.bfloat16))
+    dg, db, cs = (torch.zeros(E, device=cuda) for _ in range(3))
+    ops.ln_param_grads(dy, x, mean, rstd, dx16, dg, db, cs)
+    assert torch.allclose(dg, gr.grad, atol=1e-3 * math.sqrt(M), rtol=1e-4)
+    assert torch.allclose(db, br.grad, atol=1e-3 * math.sqrt(M), rtol=1e-4)
+    assert torch.allclose(cs, dx16.float().sum(0), atol=1e-3 * math.sqrt(M), rtol=1e-4)
+
+
 @pytest.mark.parametrize("M,E", [(472, 768), (7552, 768), (160, 512), (3, 512)])
 def test_layernorm_fwd_bwd(cuda, M, E):
     from mmtg_b200 import ops
