@@ -496,16 +496,18 @@ int attn_fwd_impl(const bf16* qkv, const int* kmask, bf16* out, float* lse, int 
 }
 
 int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
-                bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop);
+                bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop, float* dbias);
 
 int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
              cudaStream_t st, const DropSpec* drop) {
   return attn_fwd_impl(qkv, kmask, out, lse, B, L, NH, 0, st, drop);
 }
 
+// dbias (optional, [3E]): += column sums of dqkv, the c_attn bias gradient - fused into the tcgen05
+// kernel's drains, a separate pass behind the mma.sync kernels
 int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
                   float* delta, bf16* dqkv, int B, int L, int NH, int impl, cudaStream_t st,
-                  const DropSpec* drop = nullptr) {
+                  const DropSpec* drop = nullptr, float* dbias = nullptr) {
   // L <= 256: whole-head tcgen05 kernel (attention_tc.cu); longer sequences (config 5),
   // impl == 1 and MMTG_ATTN_BWD_TC=0 use the tiled mma.sync kernels below
   static const bool env_tc = []() {
@@ -519,7 +521,7 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
   if (drop_on(drop)) { p.drop_seed = drop->seed; p.drop_site = drop->site; p.drop_p = drop->p; }
   ProfScope prof(1, 2.5 * 4.0 * 64 * 0.5 * L * (L + 1.0) * B * NH, 2.0 * 8 * B * L * NH * 64, st);
   // (the whole-head tcgen05 kernel forms delta = rowsum(dO * O) in its own prologue)
-  if (use_tc && L <= 256) return attn_bwd_tc(qkv, kmask, out, dout, lse, dqkv, B, L, NH, st, drop);
+  if (use_tc && L <= 256) return attn_bwd_tc(qkv, kmask, out, dout, lse, dqkv, B, L, NH, st, drop, dbias);
   const long long warps = (long long)B * L;
   attn_delta_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, st>>>(out, dout, delta, B, L, NH, p.E);
   MMTG_LAUNCH_OK();
@@ -536,12 +538,13 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
   attn_bwd_dq_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(p);
   MMTG_LAUNCH_OK();
   count_launch(3);
+  if (dbias) MMTG_TRY(colsum(dqkv, 1, 3 * p.E, nullptr, 0, dbias, B * L, 3 * p.E, st));
   return 0;
 }
 
 int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
-             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop) {
-  return attn_bwd_impl(qkv, kmask, out, dout, lse, delta, dqkv, B, L, NH, 0, st, drop);
+             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop, float* dbias) {
+  return attn_bwd_impl(qkv, kmask, out, dout, lse, delta, dqkv, B, L, NH, 0, st, drop, dbias);
 }
 
 }  // namespace mmtg

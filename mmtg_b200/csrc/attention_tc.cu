@@ -408,6 +408,7 @@ struct AttnBwdTcParams {
   const bf16* out;      // [B*L, E] forward output O   (delta = rowsum(dO * O) is formed in the prologue)
   const bf16* dout;     // [B*L, E]
   bf16* dqkv;           // [B*L, 3E]
+  float* dbias;         // optional [3E]: += column sums of dqkv (the c_attn bias gradient), fused into the drains
   int B, L, NH, E;
   float scale;
   const unsigned long long* drop_seed;  // same mask as the forward (see AttnTcParams)
@@ -440,12 +441,37 @@ constexpr int BW_THREADS = BW_SM_WARPS * 32 + 32;    // + the control warp (TMA 
 //   dst(tile, row, col) = gbase + tile * tile_stride + row * pitch + col ; rows >= rows_valid - 128 * tile'
 //   (tile_rows_shared: both tiles cover the same rows) are skipped.
 __device__ __forceinline__ void bw_drain(uint8_t* stage, uint32_t taddr, int r, int c, float scale, uint64_t* bar_free,
-                                         bf16* gbase, long long tile_stride, long long pitch, int rows_valid, int ntiles) {
+                                         bf16* gbase, long long tile_stride, long long pitch, int rows_valid, int ntiles,
+                                         float* cs) {
   const int tile = c >> 1;
   if (tile < ntiles) {  // warp-uniform
     uint32_t v[32];
     tmem_ld_32x32(taddr, v);
     tmem_ld_wait();
+    if (cs) {
+      // column sums of this warp's 32 rows x 32 columns (rows beyond the sequence hold exact zeros:
+      // their P / dS were masked), lane t keeps column t; the four row quadrants (and both key /
+      // query blocks) meet in shared memory. Bias gradient of c_attn without a pass over dqkv.
+      // (butterfly transpose-reduce: 31 shuffles per warp; 32 separate warp sums were 160 and cost
+      // 14 us per launch - the shuffle pipe serves one warp instruction per clock per SM)
+      float w[16];
+      const int ln = r & 31;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float lo = __uint_as_float(v[i]) * scale, hi = __uint_as_float(v[i + 16]) * scale;
+        const bool up = ln & 16;
+        w[i] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+      }
+#pragma unroll
+      for (int st = 8; st >= 1; st >>= 1) {
+#pragma unroll
+        for (int i = 0; i < st; ++i) {
+          const bool up = ln & st;
+          w[i] = (up ? w[i + st] : w[i]) + __shfl_xor_sync(0xffffffffu, up ? w[i] : w[i + st], st);
+        }
+      }
+      atomicAdd(cs + (c & 1) * 32 + ln, w[0]);  // lane t holds column t
+    }
     uint8_t* srow = stage + tile * 16384 + r * 128;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -493,6 +519,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint32_t* tmem_slot = (uint32_t*)(bar_load + 6);
   uint32_t* s_kbits = (uint32_t*)(smem + BW_BAR + 64);  // [8]: bit t of word w = key 32 w + t is attendable
   float* s_delta = (float*)(smem + BW_BAR + 128);       // [256] rowsum(dO * O) of this head
+  float* s_cs = (float*)(smem + BW_BAR + 128 + 1024);   // [192] column sums of dQ | dK | dV of this head
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x;
@@ -527,6 +554,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (threadIdx.x < 192) s_cs[threadIdx.x] = 0.f;
   if (warp < 8) {  // key-padding / sequence-end mask as 8 ballot words
     const int k = warp * 32 + lane;
     const bool ok = k < p.L && (p.kmask == nullptr || p.kmask[b * p.L + k] != 0);
@@ -734,13 +762,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_wait<27>(bar_mma2, (uint32_t)((pair - 1) & 1));
       tc_fence_after();
       bw_drain(smem + BW_P, (c < 2 ? tDK : tDV) + lane_addr + (c & 1) * 32, r, c, c < 2 ? p.scale : 1.f, bar_epi,
-               p.dqkv + ((long long)row0 + j * 128) * 3 * p.E + h * 64 + p.E, p.E, 3 * p.E, p.L - j * 128, 2);
+               p.dqkv + ((long long)row0 + j * 128) * 3 * p.E + h * 64 + p.E, p.E, 3 * p.E, p.L - j * 128, 2,
+               p.dbias ? s_cs + (c < 2 ? 64 : 128) : nullptr);
       if (warp == 0) BW_STAMP(50 + j * 2);
     }
     // ---- drain dQ (all second-stage MMAs retired: bar_mma2 of the last pair was waited above):
     //      chunk c takes query block c / 2, columns 32 (c % 2) .. +31 ----
     bw_drain(smem + BW_P, tDQ + (c >> 1) * 64 + lane_addr + (c & 1) * 32, r, c, p.scale, nullptr,
-             p.dqkv + (long long)row0 * 3 * p.E + h * 64, (long long)128 * 3 * p.E, 3 * p.E, p.L, nb);
+             p.dqkv + (long long)row0 * 3 * p.E + h * 64, (long long)128 * 3 * p.E, 3 * p.E, p.L, nb,
+             p.dbias ? s_cs : nullptr);
+    // (the second named barrier inside bw_drain orders every shared-memory add before this read)
+    if (p.dbias && threadIdx.x < 192)
+      atomicAdd(p.dbias + (threadIdx.x >> 6) * p.E + h * 64 + (threadIdx.x & 63), s_cs[threadIdx.x]);
   }
   if (warp == 0) BW_STAMP(60);
   tc_fence_before();
@@ -759,7 +792,7 @@ void attn_set_clk(unsigned long long* dev) { g_attn_clk = dev; }
 
 // dqkv for L <= 256; delta = rowsum(dO * O) is formed inside the kernel from `out` and `dout`.
 int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
-                bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop) {
+                bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop, float* dbias) {
   MMTG_CHECK_ARG(L <= 256, "tcgen05 attention backward handles L <= 256");
   const int E = NH * 64;
   CUtensorMap tm_qkv, tm_do;
@@ -771,7 +804,7 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* 
     attr_set = true;
   }
   AttnBwdTcParams p;
-  p.kmask = kmask; p.lse = lse; p.out = out; p.dout = dout; p.dqkv = dqkv;
+  p.kmask = kmask; p.lse = lse; p.out = out; p.dout = dout; p.dqkv = dqkv; p.dbias = dbias;
   p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
   p.drop_seed = drop ? drop->seed : nullptr;
   p.drop_site = drop ? drop->site : 0u;

@@ -556,9 +556,10 @@ extern "C" int mmtg_train_backward(const mmtg_model* m, const mmtg_batch* b, voi
       // ---- attention ----
       MMTG_TRY(on_side([&](cudaStream_t s2) { return wgrad(L.att, E, t_g16b, E, G + lo.proj_w, E, E, E, M, s2, wg); }));
       MMTG_TRY(Gemm(t_g16b, E, false, W + lo.proj_w, E, false, M, E, E).out_bf16(t_datt, E).run(st));
-      MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, t_datt, L.lse, w.delta, t_dqkv, B, d.L, d.NH, st, &d_att));
+      // (the c_attn bias gradient = column sums of dqkv comes out of the attention backward's drains)
+      MMTG_TRY(attn_bwd(L.qkv, b->attn_mask, L.att, t_datt, L.lse, w.delta, t_dqkv, B, d.L, d.NH, st, &d_att,
+                        G + lo.attn_b));
       MMTG_TRY(on_side([&](cudaStream_t s2) {
-        MMTG_TRY(colsum(t_dqkv, 1, 3 * E, nullptr, 0, G + lo.attn_b, M, 3 * E, s2));
         return wgrad(L.x1, E, t_dqkv, 3 * E, G + lo.attn_w, 3 * E, E, 3 * E, M, s2, wg);
       }));
       MMTG_TRY(Gemm(t_dqkv, 3 * E, false, W + lo.attn_w, 3 * E, false, M, E, 3 * E).out_bf16(t_dx2, E).run(st));

@@ -36,7 +36,8 @@ int dlogits_f32_to_bf16(const float* src, bf16* dst, int M, int V, int Vp, cudaS
 int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
              cudaStream_t st, const DropSpec* drop = nullptr);
 int attn_bwd(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
-             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop = nullptr);
+             float* delta, bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop = nullptr,
+             float* dbias = nullptr);  // dbias [3E] += column sums of dqkv (c_attn bias gradient)
 
 // loss.cu
 int lse_rows(const float* logits, long long ld, float* lse, int M, int V, cudaStream_t st);
