@@ -498,6 +498,9 @@ int attn_fwd_impl(const bf16* qkv, const int* kmask, bf16* out, float* lse, int 
 int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* dout, const float* lse,
                 bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop, float* dbias);
 
+int attn_bwd_tiled_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float* lse, const float* delta,
+                      bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop, float* dbias);
+
 int attn_fwd(const bf16* qkv, const int* kmask, bf16* out, float* lse, int B, int L, int NH,
              cudaStream_t st, const DropSpec* drop) {
   return attn_fwd_impl(qkv, kmask, out, lse, B, L, NH, 0, st, drop);
@@ -525,6 +528,11 @@ int attn_bwd_impl(const bf16* qkv, const int* kmask, const bf16* out, const bf16
   const long long warps = (long long)B * L;
   attn_delta_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, st>>>(out, dout, delta, B, L, NH, p.E);
   MMTG_LAUNCH_OK();
+  // 256 < L <= 1024: tiled tcgen05 kernels (dK/dV per key block, dQ per query block)
+  if (use_tc && L <= 1024) {
+    count_launch();
+    return attn_bwd_tiled_tc(qkv, kmask, dout, lse, delta, dqkv, B, L, NH, st, drop, dbias);
+  }
   dim3 grid(cdiv(L, BQ), B * NH);
   constexpr int BWD_SMEM = 6 * BQ * HD * 2 + 4 * BQ * 4;  // 6 bf16 tiles + 4 x 64 floats
   MMTG_PER_DEVICE_FLAG(attr_set);
@@ -561,7 +569,7 @@ extern "C" int mmtg_attn_bwd_ex(const void* qkv, const int32_t* key_mask, const 
                                 int32_t B, int32_t L, int32_t n_head, int32_t impl, void* stream) {
   MMTG_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && L > 0 && n_head > 0 && impl >= 0 && impl <= 2,
                  "bad attention bwd args");
-  MMTG_CHECK_ARG(!(impl == 2 && L > 256), "tcgen05 attention backward handles L <= 256");
+  MMTG_CHECK_ARG(!(impl == 2 && L > 1024), "tcgen05 attention backward handles L <= 1024");
   return attn_bwd_impl((const bf16*)qkv, key_mask, (const bf16*)out, (const bf16*)dout, lse, delta_ws,
                        (bf16*)dqkv, B, L, n_head, impl, (cudaStream_t)stream);
 }
@@ -581,7 +589,7 @@ extern "C" int mmtg_attn_bwd_drop(const void* qkv, const int32_t* key_mask, cons
                                   void* stream) {
   MMTG_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && L > 0 && n_head > 0 && p >= 0.f &&
                      p < 1.f && impl >= 0 && impl <= 2, "bad attention bwd args");
-  MMTG_CHECK_ARG(!(impl == 2 && L > 256), "tcgen05 attention backward handles L <= 256");
+  MMTG_CHECK_ARG(!(impl == 2 && L > 1024), "tcgen05 attention backward handles L <= 1024");
   DropSpec d{(const unsigned long long*)seed_dev, site, p, 0};
   return attn_bwd_impl((const bf16*)qkv, key_mask, (const bf16*)out, (const bf16*)dout, lse, delta_ws,
                        (bf16*)dqkv, B, L, n_head, impl, (cudaStream_t)stream, &d);

@@ -785,6 +785,287 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   if (warp == 0) BW_STAMP(61);
 }
 
+
+// =============================================================================================
+// tcgen05 attention BACKWARD for longer sequences (256 < L <= 1024, BASELINE.json configs[4]):
+// the whole head no longer fits one CTA's shared memory, so the work is tiled the FlashAttention-2
+// way, in two launches of one template (MODE):
+//   MODE 0 (dK / dV): CTA = (head, key block j). K_j, V_j stay resident; Q_i, dO_i of the query
+//          blocks i >= j stream through a two-stage TMA ring. Per step: S = Q_i K_j^T,
+//          dP = dO_i V_j^T -> P, dS (16 softmax warps, as in the whole-head kernel) ->
+//          dV_j += P^T dO_i, dK_j += dS^T Q_i accumulate in TMEM; drained once at the end.
+//   MODE 1 (dQ):      CTA = (head, query block i). Q_i, dO_i resident; K_j, V_j of the key blocks
+//          j <= i stream. Per step S, dP -> dS -> dQ_i += dS K_j in TMEM.
+// S / dP are computed twice (once per mode) instead of combining dQ partials of different CTAs in
+// atomics: every output element is written once, by one CTA, in a fixed order (deterministic).
+// delta = rowsum(dO * O) comes from attn_delta_kernel (one pass; every CTA of a head needs it).
+// smem: resident 2 x 16 KB | ring 2 x (2 x 16 KB) | P 32 KB | dS 32 KB = 160 KB; TMEM S 128 +
+// dP 128 + two 64-column accumulators.
+// =============================================================================================
+constexpr int BT_RES = 0, BT_RING = 32768, BT_P = 98304, BT_DS = 131072, BT_BAR = 163840;
+constexpr int BT_SMEM_TOTAL = BT_BAR + 2048 + 1024;
+
+struct AttnBwdTiledParams {
+  const int* kmask;     // [B, L]
+  const float* lse;     // [B, NH, L]
+  const float* delta;   // [B, NH, L]
+  bf16* dqkv;           // [B*L, 3E]
+  float* dbias;         // optional [3E]
+  int B, L, NH, E;
+  float scale;
+  const unsigned long long* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+attn_bwd_tiled_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                         const AttnBwdTiledParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar_res = (uint64_t*)(smem + BT_BAR);  // resident tiles landed
+  uint64_t* bar_full = bar_res + 1;                // [2] ring stage landed
+  uint64_t* bar_sdp = bar_res + 3;
+  uint64_t* bar_pds = bar_res + 4;                 // 512 arrivals
+  uint64_t* bar_mma2 = bar_res + 5;
+  uint32_t* tmem_slot = (uint32_t*)(bar_res + 6);
+  uint32_t* s_kbits = (uint32_t*)(smem + BT_BAR + 64);   // [32]: all keys of the sequence (<= 1024)
+  float* s_cs = (float*)(smem + BT_BAR + 256);           // [128]: column sums of the two accumulator tiles
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = cdiv(p.L, 128);
+  const int bh = blockIdx.y;
+  const int b = bh / p.NH, h = bh - b * p.NH;
+  // heavy CTAs first: MODE 0 key block j walks nb - j query blocks, MODE 1 query block i walks i + 1 key blocks
+  const int blk = MODE == 0 ? (int)blockIdx.x : nb - 1 - (int)blockIdx.x;
+  const int ns = MODE == 0 ? nb - blk : blk + 1;
+  const int row0 = b * p.L;
+  // block index streamed at step s / the (query block i, key block j) of the step
+  auto stream_blk = [&](int s) { return MODE == 0 ? blk + s : s; };
+
+  if (warp == BW_SM_WARPS) {
+    if (lane == 0) {
+      mbar_init(bar_res, 1);
+      mbar_init(&bar_full[0], 1);
+      mbar_init(&bar_full[1], 1);
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_pds, BW_SM_WARPS * 32);
+      mbar_init(bar_mma2, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      mbar_arrive_expect_tx(bar_res, 2 * 16384);
+      if (MODE == 0) {
+        tma_load_2d(smem + BT_RES, &tm_qkv, bar_res, p.E + h * 64, row0 + blk * 128);              // K_j
+        tma_load_2d(smem + BT_RES + 16384, &tm_qkv, bar_res, 2 * p.E + h * 64, row0 + blk * 128);  // V_j
+      } else {
+        tma_load_2d(smem + BT_RES, &tm_qkv, bar_res, h * 64, row0 + blk * 128);                    // Q_i
+        tma_load_2d(smem + BT_RES + 16384, &tm_do, bar_res, h * 64, row0 + blk * 128);             // dO_i
+      }
+      for (int s = 0; s < 2 && s < ns; ++s) {
+        uint8_t* ring = smem + BT_RING + s * 32768;
+        const int sb = stream_blk(s);
+        mbar_arrive_expect_tx(&bar_full[s], 2 * 16384);
+        if (MODE == 0) {
+          tma_load_2d(ring, &tm_qkv, &bar_full[s], h * 64, row0 + sb * 128);           // Q_i
+          tma_load_2d(ring + 16384, &tm_do, &bar_full[s], h * 64, row0 + sb * 128);    // dO_i
+        } else {
+          tma_load_2d(ring, &tm_qkv, &bar_full[s], p.E + h * 64, row0 + sb * 128);         // K_j
+          tma_load_2d(ring + 16384, &tm_qkv, &bar_full[s], 2 * p.E + h * 64, row0 + sb * 128);  // V_j
+        }
+      }
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < 128) s_cs[threadIdx.x] = 0.f;
+  for (int w0 = warp; w0 < nb * 4; w0 += BW_THREADS / 32) {  // key mask of the whole row as ballot words
+    const int k = w0 * 32 + lane;
+    const bool ok = k < p.L && (p.kmask == nullptr || p.kmask[b * p.L + k] != 0);
+    const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_kbits[w0] = bits;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tA0 = tmem_base + 256, tA1 = tmem_base + 320;
+
+  if (warp == BW_SM_WARPS) {
+    if (lane == 0) {
+      const uint32_t idesc_sp = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_kv = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);
+      const uint32_t aRes0 = smem_u32(smem + BT_RES), aRes1 = aRes0 + 16384;
+      const uint32_t aP = smem_u32(smem + BT_P), aDS = smem_u32(smem + BT_DS);
+      auto issue_sdp = [&](int s) {
+        const uint32_t r0a = smem_u32(smem + BT_RING + (s & 1) * 32768), r1a = r0a + 16384;
+        // MODE 0: S = Q_i(ring0) K_j(res0)^T, dP = dO_i(ring1) V_j(res1)^T; MODE 1: Q_i / dO_i resident, K_j / V_j in the ring
+        const uint64_t dQk = umma_desc_sw128(MODE == 0 ? r0a : aRes0, 16, 1024);
+        const uint64_t dKk = umma_desc_sw128(MODE == 0 ? aRes0 : r0a, 16, 1024);
+        const uint64_t dOk = umma_desc_sw128(MODE == 0 ? r1a : aRes1, 16, 1024);
+        const uint64_t dVk = umma_desc_sw128(MODE == 0 ? aRes1 : r1a, 16, 1024);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS, dQk + 2 * k, dKk + 2 * k, idesc_sp, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tDP, dOk + 2 * k, dVk + 2 * k, idesc_sp, k > 0 ? 1u : 0u);
+        umma_commit(bar_sdp);
+      };
+      mbar_wait<31>(bar_res, 0);
+      mbar_wait<32>(&bar_full[0], 0);
+      issue_sdp(0);
+      for (int s = 0; s < ns; ++s) {
+        mbar_wait<33>(bar_pds, (uint32_t)(s & 1));
+        tc_fence_after();
+        const uint32_t r0a = smem_u32(smem + BT_RING + (s & 1) * 32768), r1a = r0a + 16384;
+        const uint32_t acc = s > 0 ? 1u : 0u;
+        if (MODE == 0) {
+          const uint64_t dPm = umma_desc_sw128(aP, 16384, 1024), dSm = umma_desc_sw128(aDS, 16384, 1024);
+          const uint64_t dOm = umma_desc_sw128(r1a, 8192, 1024), dQm = umma_desc_sw128(r0a, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16(tA1, dPm + 128 * k, dOm + 128 * k, idesc_kv, k > 0 ? 1u : acc);  // dV_j += P^T dO_i
+            umma_bf16(tA0, dSm + 128 * k, dQm + 128 * k, idesc_kv, k > 0 ? 1u : acc);  // dK_j += dS^T Q_i
+          }
+        } else {
+          const uint64_t dSk = umma_desc_sw128(aDS, 16, 1024), dKm = umma_desc_sw128(r0a, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dQ_i += dS K_j
+            umma_bf16(tA0, dSk + (k >> 2) * 1024 + (k & 3) * 2, dKm + 128 * k, idesc_dq, k > 0 ? 1u : acc);
+        }
+        umma_commit(bar_mma2);
+        if (s + 1 < ns) {
+          mbar_wait<34>(&bar_full[(s + 1) & 1], (uint32_t)(((s + 1) >> 1) & 1));
+          issue_sdp(s + 1);
+        }
+        if (s + 2 < ns) {  // ring stage s & 1 is free once this step's gradient MMAs have retired
+          mbar_wait<35>(bar_mma2, (uint32_t)(s & 1));
+          uint8_t* ring = smem + BT_RING + (s & 1) * 32768;
+          const int sb = stream_blk(s + 2);
+          mbar_arrive_expect_tx(&bar_full[s & 1], 2 * 16384);
+          if (MODE == 0) {
+            tma_load_2d(ring, &tm_qkv, &bar_full[s & 1], h * 64, row0 + sb * 128);
+            tma_load_2d(ring + 16384, &tm_do, &bar_full[s & 1], h * 64, row0 + sb * 128);
+          } else {
+            tma_load_2d(ring, &tm_qkv, &bar_full[s & 1], p.E + h * 64, row0 + sb * 128);
+            tma_load_2d(ring + 16384, &tm_qkv, &bar_full[s & 1], 2 * p.E + h * 64, row0 + sb * 128);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3, c = warp >> 2;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    const int hoff = (c >> 1) * 16384;
+    uint8_t* prow = smem + BT_P + r * 128 + hoff;
+    uint8_t* dsrow = smem + BT_DS + r * 128 + hoff;
+    const bool dropping = p.drop_p > 0.f;
+    DropKey dk = {0u, 0u, 0u, 1.f};
+    if (dropping) dk = drop_key(p.drop_seed, p.drop_site, p.drop_p);
+    const long long stat0 = ((long long)b * p.NH + h) * p.L;
+    auto row_stats = [&](int i, float& nlse2, float& dl) {
+      const int q = i * 128 + r;
+      nlse2 = -INFINITY;
+      dl = 0.f;
+      if (q < p.L) {
+        const float lv = __ldg(p.lse + stat0 + q);
+        nlse2 = lv == -INFINITY ? -INFINITY : -lv * LOG2E;
+        dl = __ldg(p.delta + stat0 + q);
+      }
+    };
+    float nlse2, dl;
+    row_stats(MODE == 0 ? blk : blk, nlse2, dl);  // MODE 0: first query block = the diagonal one (i = j)
+    for (int s = 0; s < ns; ++s) {
+      const int i = MODE == 0 ? blk + s : blk, j = MODE == 0 ? blk : s;
+      const int q = i * 128 + r;
+      float nlse2_n = nlse2, dl_n = dl;
+      if (MODE == 0 && s + 1 < ns) row_stats(i + 1, nlse2_n, dl_n);  // next step's rows, fetched a step ahead
+      const uint32_t kbits = s_kbits[j * 4 + c];
+      mbar_wait<36>(bar_sdp, (uint32_t)(s & 1));
+      tc_fence_after();
+      if (i == j && c > qd) {  // warp-uniform: chunk entirely in the causal future
+        if (s > 0) mbar_wait<37>(bar_mma2, (uint32_t)((s - 1) & 1));
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int off = (((c & 1) * 4 + t) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      } else {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, sv);
+        tmem_ld_32x32(tDP + lane_addr + c * 32, dv);
+        uint32_t vm = kbits;
+        if (i == j) {
+          const int lim = r - c * 32;
+          if (lim < 31) vm &= (2u << lim) - 1u;
+        }
+        const uint32_t pair0 = (uint32_t)((b * p.NH + h) * p.L + q) * (uint32_t)((p.L + 1) >> 1) +
+                               (uint32_t)((j * 128 + c * 32) >> 1);
+        tmem_ld_wait();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          float dm0 = 1.f, dm1 = 1.f;
+          if (dropping) {
+            const uint32_t bits = drop_bits(dk, pair0 + (uint32_t)(t >> 1));
+            dm0 = drop_keep_lo(dk, bits) ? dk.inv_keep : 0.f;
+            dm1 = drop_keep_hi(dk, bits) ? dk.inv_keep : 0.f;
+          }
+          const float x0 = ((vm >> t) & 1u) ? fmaf(__uint_as_float(sv[t]), sl2, nlse2) : -INFINITY;
+          const float x1 = ((vm >> (t + 1)) & 1u) ? fmaf(__uint_as_float(sv[t + 1]), sl2, nlse2) : -INFINITY;
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          const float pe0 = p0 * dm0, pe1 = p1 * dm1;
+          const float de0 = p0 * fmaf(__uint_as_float(dv[t]), dm0, -dl);
+          const float de1 = p1 * fmaf(__uint_as_float(dv[t + 1]), dm1, -dl);
+          __nv_bfloat162 a = __floats2bfloat162_rn(pe0, pe1), d2 = __floats2bfloat162_rn(de0, de1);
+          pp[t >> 1] = *reinterpret_cast<uint32_t*>(&a);
+          pd[t >> 1] = *reinterpret_cast<uint32_t*>(&d2);
+        }
+        if (s > 0) mbar_wait<37>(bar_mma2, (uint32_t)((s - 1) & 1));  // P / dS of the previous step consumed
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int off = (((c & 1) * 4 + t) ^ (r & 7)) << 4;
+          if (MODE == 0) *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[4 * t], pp[4 * t + 1], pp[4 * t + 2], pp[4 * t + 3]);
+          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(pd[4 * t], pd[4 * t + 1], pd[4 * t + 2], pd[4 * t + 3]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+      nlse2 = nlse2_n;
+      dl = dl_n;
+    }
+    // ---- drain the accumulators ----
+    mbar_wait<38>(bar_mma2, (uint32_t)((ns - 1) & 1));
+    tc_fence_after();
+    if (MODE == 0) {  // chunk 0,1: dK_j columns, 2,3: dV_j columns; TMEM lane r = key blk*128 + r
+      bw_drain(smem + BT_P, (c < 2 ? tA0 : tA1) + lane_addr + (c & 1) * 32, r, c, c < 2 ? p.scale : 1.f, nullptr,
+               p.dqkv + ((long long)row0 + blk * 128) * 3 * p.E + h * 64 + p.E, p.E, 3 * p.E, p.L - blk * 128, 2,
+               p.dbias ? s_cs + (c < 2 ? 0 : 64) : nullptr);
+      if (p.dbias && threadIdx.x < 128)
+        atomicAdd(p.dbias + (1 + (threadIdx.x >> 6)) * p.E + h * 64 + (threadIdx.x & 63), s_cs[threadIdx.x]);
+    } else {  // dQ_i: one tile, chunks 0 and 1
+      bw_drain(smem + BT_P, tA0 + lane_addr + (c & 1) * 32, r, c, p.scale, nullptr,
+               p.dqkv + ((long long)row0 + blk * 128) * 3 * p.E + h * 64, (long long)128 * 3 * p.E, 3 * p.E,
+               p.L - blk * 128, 1, p.dbias ? s_cs : nullptr);
+      if (p.dbias && threadIdx.x < 64) atomicAdd(p.dbias + h * 64 + threadIdx.x, s_cs[threadIdx.x]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == BW_SM_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 static unsigned long long* g_attn_clk = nullptr;
@@ -813,6 +1094,35 @@ int attn_bwd_tc(const bf16* qkv, const int* kmask, const bf16* out, const bf16* 
   attn_bwd_tc_kernel<<<B * NH, BW_THREADS, BW_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
   MMTG_LAUNCH_OK();
   count_launch();
+  return 0;
+}
+
+// dqkv for 256 < L <= 1024 (delta must hold rowsum(dO * O): attn_delta_kernel)
+int attn_bwd_tiled_tc(const bf16* qkv, const int* kmask, const bf16* dout, const float* lse, const float* delta,
+                      bf16* dqkv, int B, int L, int NH, cudaStream_t st, const DropSpec* drop, float* dbias) {
+  MMTG_CHECK_ARG(L <= 1024, "tcgen05 attention backward handles L <= 1024");
+  const int E = NH * 64;
+  CUtensorMap tm_qkv, tm_do;
+  MMTG_TRY(make_tmap_bf16_2d(&tm_qkv, qkv, (uint64_t)3 * E, (uint64_t)B * L, (uint64_t)3 * E, 64, 128));
+  MMTG_TRY(make_tmap_bf16_2d(&tm_do, dout, (uint64_t)E, (uint64_t)B * L, (uint64_t)E, 64, 128));
+  MMTG_PER_DEVICE_FLAG(attr_set);
+  if (!attr_set) {
+    MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tiled_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM_TOTAL));
+    MMTG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tiled_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM_TOTAL));
+    attr_set = true;
+  }
+  AttnBwdTiledParams p;
+  p.kmask = kmask; p.lse = lse; p.delta = delta; p.dqkv = dqkv; p.dbias = dbias;
+  p.B = B; p.L = L; p.NH = NH; p.E = E; p.scale = 0.125f;
+  p.drop_seed = drop ? drop->seed : nullptr;
+  p.drop_site = drop ? drop->site : 0u;
+  p.drop_p = (drop && drop->seed) ? drop->p : 0.f;
+  dim3 grid(cdiv(L, 128), B * NH);
+  attn_bwd_tiled_tc_kernel<0><<<grid, BW_THREADS, BT_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
+  MMTG_LAUNCH_OK();
+  attn_bwd_tiled_tc_kernel<1><<<grid, BW_THREADS, BT_SMEM_TOTAL, st>>>(tm_qkv, tm_do, p);
+  MMTG_LAUNCH_OK();
+  count_launch(2);
   return 0;
 }
 
