@@ -365,7 +365,7 @@ def measure_decode(args, dev, cpu_baseline=True):
         "roofline": {"bound": "hbm", "achieved": gbytes / sec, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": gbytes / sec / pk["hbm_gbs"], "traffic": traffic,
                      "x_of_floor": sec / (gbytes / pk["hbm_gbs"]),
-                     "kernel": "decode_mega_kernel (one persistent launch per position); algorithmic bytes = bf16 weights + K/V per position, whole call",
+                     "kernel": "decode_mega_kernel (ONE persistent launch for all decoded positions of a call: embedding, projector, 12 blocks, lm_head and sampler in-kernel, grid barriers between phases); algorithmic bytes = bf16 weights + K/V per position, whole call",
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_src})"},
         "topk_preset_tokens_per_s": B * LENGTH / res["topk10_p0.7"][0],
     }

@@ -31,10 +31,17 @@ if len(rows) > 2:
     ins = hdr.index("# Samples")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     agg = {}
+    data = [r for r in data if len(r) > max(stall_cols + [ins])]  # (multi-kernel reports repeat the header block)
+
+    def _int(x):
+        try:
+            return int(x or 0)
+        except ValueError:
+            return 0
     for r in data:
         for i in stall_cols:
-            agg[hdr[i]] = agg.get(hdr[i], 0) + int(r[i] or 0)
-    tot = sum(int(r[ins] or 0) for r in data)
+            agg[hdr[i]] = agg.get(hdr[i], 0) + _int(r[i])
+    tot = sum(_int(r[ins]) for r in data)
     lines.append(f"  warp-state samples: {tot}")
     for k, v in sorted(agg.items(), key=lambda x: -x[1])[:8]:
         lines.append(f"    {k}: {v} ({100.0 * v / max(tot, 1):.1f} %)")
