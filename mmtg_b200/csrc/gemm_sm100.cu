@@ -1020,9 +1020,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  static const bool use_pdl = []() {  // MMTG_GEMM_PDL=0 disables programmatic dependent launch
+  // Programmatic dependent launch (the next GEMM's CTAs are scheduled while this one drains and run
+  // their TMEM / barrier prologue early). MEASURED in round 2 on the full train step: 8.25 ms with it,
+  // 8.00-8.03 ms without (same box, two runs each) - the early CTAs hold whole SMs (227 KB of shared
+  // memory) while they wait, which the side stream's weight-gradient GEMMs could have used. Opt-in:
+  // MMTG_GEMM_PDL=1. (The griddepcontrol instructions in the kernel are no-ops without the attribute.)
+  static const bool use_pdl = []() {
     const char* e = getenv("MMTG_GEMM_PDL");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
