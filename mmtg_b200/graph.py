@@ -121,6 +121,7 @@ class GraphedTrainStep:
             return self.total
         self.g_fwd.replay()
         for g, s0, s1 in self.g_stage:
+            self.sync.before_stages(self.model, s0, s1, self.nstage)
             g.replay()
             for s in range(s0, s1):
                 self.sync.after_stage(self.model, s, self.nstage)

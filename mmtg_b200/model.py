@@ -299,6 +299,11 @@ class MMTG(nn.Module):
     def tail_bucket(self):
         return self._layers_flat_end, self._flat_numel
 
+    def wte_range(self):
+        """[lo, hi) element range of the tied wte / lm_head weight (last in the flat order) and its row width."""
+        lo, n = self._layout["decoder.gpt2.transformer.wte.weight"]
+        return lo, lo + n, self.decoder.config["n_embd"]
+
     def tail_buckets(self):
         """The tail split where the backward splits it: (projector, wpe, ln_f, tied wte) are final
         after stage NL+1, (encoder, multi-modal attention) after stage NL+2."""
@@ -760,6 +765,7 @@ def _run_backward(step, gkl):
                    "mmtg_train_backward")
         return
     for s in range(nstage):
+        sync.before_stages(mdl, s, s + 1, nstage)
         rc = lib.mmtg_train_backward(C.byref(step.cm), C.byref(step.cb), wsp, C.c_int64(step.ws.numel()),
                                      C.c_void_p(gkl.data_ptr()) if gkl is not None else None, s, s + 1, st)
         _lib.check(rc, "mmtg_train_backward")

@@ -43,6 +43,7 @@ class GradSync:
                 else torch.bfloat16
         self.grad_dtype = grad_dtype
         self._wire = None  # bf16 staging buffer, same offsets as the flat gradient buffer
+        self._wte_saved, self._wte_evt = None, None  # early all-reduce of the tied wte gradient (after_stage)
 
     def _reduce(self, t):
         if self.world == 1 or t.numel() == 0:
@@ -76,15 +77,53 @@ class GradSync:
         o = t.storage_offset()
         return self._wire[o:o + t.numel()]
 
+    # Rows of the tied wte that the embedding backward (token-TYPE embeddings, stage NL+1) can touch.
+    # The gradient of wte is the lm_head weight gradient (all 13,317 rows, final after stage 0) plus
+    # the type-embedding rows; type ids are sentence indices (src/MyDataset.py: <= max_seq_length /
+    # sent_len + 1), far below this bound.
+    WTE_TYPE_ROWS = 64
+
+    def before_stages(self, model, s0, s1, nstage):
+        """Called before backward stages [s0, s1) are issued on the current stream."""
+        nl = nstage - 3
+        if self._wte_saved is not None and s0 <= nl + 1 < s1 and self._wte_evt is not None:
+            # the embedding stage adds into wte rows the early all-reduce has already saved and cleared
+            torch.cuda.current_stream().wait_event(self._wte_evt)
+
     def after_stage(self, model, stage, nstage):
         G = model._flat[2]
         nl = nstage - 3
-        if 1 <= stage <= nl:
+        early_wte = self.world > 1 and G.is_cuda and hasattr(model, "wte_range")
+        if stage == 0 and early_wte:
+            # The tied wte / lm_head gradient (41 MB, the largest single tensor) is all-reduced NOW, under the
+            # whole decoder backward, instead of in the exposed tail: by linearity the type-embedding rows that
+            # stage NL+1 still adds are reduced separately - the reduced head part of those rows is set aside and
+            # the rows are cleared (so the tail bucket carries only the embedding contribution), and added back
+            # after the tail all-reduce.
+            lo, hi, E = model.wte_range()
+            rows = min(self.WTE_TYPE_ROWS, (hi - lo) // E)
+            self._reduce(G[lo:hi])
+            with torch.cuda.stream(self.comm_stream):
+                head = G[lo:lo + rows * E]
+                if self._wte_saved is None or self._wte_saved.numel() != head.numel():
+                    self._wte_saved = torch.empty_like(head)
+                self._wte_saved.copy_(head)
+                head.zero_()
+                self._wte_evt = torch.cuda.Event()
+                self._wte_evt.record()
+        elif 1 <= stage <= nl:
             lo, hi = model.layer_bucket(nl - stage)
             self._reduce(G[lo:hi])
-        elif stage == nl + 1:  # projector, wpe, ln_f, tied wte: reduced while the encoder side runs
+        elif stage == nl + 1:  # projector, wpe, ln_f (+ the type rows of wte): reduced while the encoder side runs
             lo, hi = model.tail_buckets()[0]
-            self._reduce(G[lo:hi])
+            if early_wte and self._wte_saved is not None:
+                wlo, _whi, E = model.wte_range()
+                hi = wlo + self._wte_saved.numel()
+                self._reduce(G[lo:hi])
+                with torch.cuda.stream(self.comm_stream):
+                    G[wlo:hi].add_(self._wte_saved)
+            else:
+                self._reduce(G[lo:hi])
         elif stage == nl + 2:  # encoder + multi-modal attention
             lo, hi = model.tail_buckets()[1]
             self._reduce(G[lo:hi])
