@@ -83,6 +83,16 @@ class GradSync:
     # sent_len + 1), far below this bound.
     WTE_TYPE_ROWS = 64
 
+    def _type_rows_ok(self, model):
+        """The early wte all-reduce is only valid when every token-type id the dataset can produce lies in the
+        first WTE_TYPE_ROWS rows (src/MyDataset.py: type ids are sentence indices 1 .. max_seq_length // sent_len
+        + 1); otherwise the tied gradient goes with the tail bucket as before."""
+        try:
+            dc = model.data_config
+            return dc["max_seq_length"] // (dc["max_sent_length"] + 2) + 2 <= self.WTE_TYPE_ROWS
+        except Exception:
+            return False
+
     def before_stages(self, model, s0, s1, nstage):
         """Called before backward stages [s0, s1) are issued on the current stream."""
         nl = nstage - 3
@@ -93,7 +103,7 @@ class GradSync:
     def after_stage(self, model, stage, nstage):
         G = model._flat[2]
         nl = nstage - 3
-        early_wte = self.world > 1 and G.is_cuda and hasattr(model, "wte_range")
+        early_wte = self.world > 1 and G.is_cuda and hasattr(model, "wte_range") and self._type_rows_ok(model)
         if stage == 0 and early_wte:
             # The tied wte / lm_head gradient (41 MB, the largest single tensor) is all-reduced NOW, under the
             # whole decoder backward, instead of in the exposed tail: by linearity the type-embedding rows that
