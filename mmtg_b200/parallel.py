@@ -68,6 +68,11 @@ class GradSync:
             if self.average:
                 t.div_(self.world)
 
+    def _on_comm(self, t):
+        """Context for small follow-up ops that must run after the collective just issued for `t`."""
+        import contextlib
+        return torch.cuda.stream(self.comm_stream) if t.is_cuda else contextlib.nullcontext()
+
     def _wire_view(self, t):
         """bf16 staging slice for the gradient slice `t` (one buffer, allocated once: the caching
         allocator must not hand out memory that a CUDA-graph pool owns)."""
@@ -103,7 +108,7 @@ class GradSync:
     def after_stage(self, model, stage, nstage):
         G = model._flat[2]
         nl = nstage - 3
-        early_wte = self.world > 1 and G.is_cuda and hasattr(model, "wte_range") and self._type_rows_ok(model)
+        early_wte = self.world > 1 and hasattr(model, "wte_range") and self._type_rows_ok(model)
         if stage == 0 and early_wte:
             # The tied wte / lm_head gradient (41 MB, the largest single tensor) is all-reduced NOW, under the
             # whole decoder backward, instead of in the exposed tail: by linearity the type-embedding rows that
@@ -113,14 +118,15 @@ class GradSync:
             lo, hi, E = model.wte_range()
             rows = min(self.WTE_TYPE_ROWS, (hi - lo) // E)
             self._reduce(G[lo:hi])
-            with torch.cuda.stream(self.comm_stream):
+            with self._on_comm(G):
                 head = G[lo:lo + rows * E]
-                if self._wte_saved is None or self._wte_saved.numel() != head.numel():
+                if self._wte_saved is None or self._wte_saved.numel() != head.numel() or self._wte_saved.device != head.device:
                     self._wte_saved = torch.empty_like(head)
                 self._wte_saved.copy_(head)
                 head.zero_()
-                self._wte_evt = torch.cuda.Event()
-                self._wte_evt.record()
+                if G.is_cuda:
+                    self._wte_evt = torch.cuda.Event()
+                    self._wte_evt.record()
         elif 1 <= stage <= nl:
             lo, hi = model.layer_bucket(nl - stage)
             self._reduce(G[lo:hi])
@@ -130,7 +136,7 @@ class GradSync:
                 wlo, _whi, E = model.wte_range()
                 hi = wlo + self._wte_saved.numel()
                 self._reduce(G[lo:hi])
-                with torch.cuda.stream(self.comm_stream):
+                with self._on_comm(G):
                     G[wlo:hi].add_(self._wte_saved)
             else:
                 self._reduce(G[lo:hi])

@@ -17,10 +17,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_allreduced_gradients_equal_single_rank_gradients(cuda, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "ddp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    lines, r = [], None
+    for port in ("29533", "29547"):  # a launcher / rendezvous failure (no worker output at all) is retried once
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", port, os.path.join(ROOT, "tests", "ddp_worker.py")]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+        lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+        if lines or r.returncode == 0:
+            break
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, f"ddp_grad_check_n{world}.json"), "w") as f:

@@ -61,6 +61,41 @@ def _worker(rank, world, port):
         s2.after_stage(m2, s, m2.nl + 3)
     want = (3 * 1 + 5 * 2) / 8.0  # gradient of the mean over the 8 concatenated rows
     assert torch.allclose(m2._flat[2], torch.full_like(m2._flat[2], want))
+    # early all-reduce of the tied wte gradient (parallel.GradSync.after_stage): the head part is reduced after
+    # stage 0, the type-embedding rows the embedding stage adds LATER are reduced with the tail bucket; the result
+    # must equal the plain average of the final per-rank gradients
+    E, V = 8, 200
+
+    class _TiedModel(_FakeModel):
+        data_config = {"max_seq_length": 220, "max_sent_length": 20}
+
+        def wte_range(self):
+            lo, hi = self.tail_bucket()
+            return hi - V * E, hi, E
+
+        def tail_buckets(self):
+            lo, hi = self.tail_bucket()
+            return (lo + 40, hi), (lo, lo + 40)  # (projector.. + wte), (encoder)
+
+    m3 = _TiedModel(nl=3, per_layer=50, tail=40 + 24 + V * E, rank=rank)
+    G3 = m3._flat[2]
+    g = torch.Generator().manual_seed(100 + rank)
+    final = torch.randn(G3.numel(), generator=g)            # this rank's final gradient
+    wlo, whi, _ = m3.wte_range()
+    type_part = torch.zeros_like(final)
+    type_part[wlo:wlo + 12 * E] = torch.randn(12 * E, generator=g)  # rows 0..11 get type-embedding gradient
+    G3.copy_(final - type_part)                               # state after stage 0: everything but the type rows
+    s3 = GradSync()
+    ns3 = m3.nl + 3
+    for s in range(ns3):
+        s3.before_stages(m3, s, s + 1, ns3)
+        if s == m3.nl + 1:
+            G3.add_(type_part)                                # the embedding stage adds into (cleared) wte rows
+        s3.after_stage(m3, s, ns3)
+    s3.finish(m3)
+    both = [torch.empty_like(final) for _ in range(world)]
+    dist.all_gather(both, final)
+    assert torch.allclose(G3, sum(both) / world, atol=1e-6), (G3 - sum(both) / world).abs().max()
     dist.destroy_process_group()
 
 
