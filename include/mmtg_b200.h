@@ -156,7 +156,7 @@ int mmtg_attn_bwd(const void* qkv, const int32_t* key_mask, const void* out, con
                   const float* lse, float* delta_ws, void* dqkv, int32_t B, int32_t L,
                   int32_t n_head, void* stream);
 /* explicit kernel choice (tests / profiling): impl 0 = default, 1 = mma.sync tiles, 2 = tcgen05/TMEM
- * (forward: any L; backward: L <= 256, whole head per CTA) */
+ * (forward: any L <= 1024; backward: whole head per CTA for L <= 256, tiled dK/dV + dQ kernels up to L = 1024) */
 /* debugging aid: per-(block, warp) progress codes written to host-mapped memory (null = off) */
 void mmtg_attn_set_trace(int32_t* host_mapped);
 /* debugging aid: CTA 0 of the tcgen05 attention backward stamps %globaltimer (ns) at its stage

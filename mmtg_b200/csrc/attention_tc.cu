@@ -2,13 +2,17 @@
 // Replaces HF GPT2Attention's SDPA forward (transformers modeling_gpt2.py:54-72).
 //
 // One CTA per (128-query tile, batch row, head); 2 CTAs per SM (80 KB smem, 256 TMEM columns).
-//   warp 4 (one elected thread): TMA loads of Q / K_j / V_j straight out of the c_attn output
-//           [B*L, 3E] (one tensor map, three column offsets), issues S = Q K_j^T
-//           (tcgen05.mma 128x128x64 into TMEM) and O += P V_j (128x64x128, V consumed MN-major);
-//   warps 0-3 (128 threads = 128 TMEM lanes = 128 query rows): tcgen05.ld their S row, mask,
-//           online softmax in the exp2 domain, write P as bf16 into SWIZZLE_128B shared memory
-//           (the A operand of the second MMA), rescale O in TMEM when the running max moves,
-//           and finally normalise / store O and the row log-sum-exp.
+//   control warp (warp 8, one elected thread): sets up the barriers and puts Q, K_0, V_0 in flight
+//           before anything else (TMA straight out of the c_attn output [B*L, 3E]: one tensor map,
+//           three column offsets), issues S = Q K_j^T (tcgen05.mma 128x128x64 into TMEM) and
+//           O += P V_j (128x64x128, V consumed MN-major); K_{j+1} streams in as soon as S(j)
+//           retires, V_{j+1} after PV(j);
+//   warps 0-7 (TWO threads per query row: warp w owns TMEM lane quadrant w % 4 and key half w / 4
+//           of every block): tcgen05.ld their part of the S row, mask (ballot words), online
+//           softmax in the exp2 domain with the row max / sum exchanged through shared memory,
+//           P as bf16 into SWIZZLE_128B shared memory (the A operand of the second MMA), O rescaled
+//           in TMEM when the running max moves, and finally O leaves through a shared-memory
+//           transpose (full 128-byte lines per warp store) with the row log-sum-exp.
 // Keys are processed in blocks of 128; the default sequence (L = 236) needs at most two.
 #include <stdlib.h>
 

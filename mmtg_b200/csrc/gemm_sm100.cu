@@ -8,9 +8,12 @@
 //    128-row tiles of the same column block, so the B tile is fetched ONCE per pair — each CTA
 //    loads half of it and TMA-multicasts it into both CTAs' shared memory (the mainloop is
 //    L2-bandwidth bound otherwise: 48 KB per CTA per k-block -> 32 KB);
-//  * static round-robin of the clusters over (tile pair, k-split) work units;
+//  * static round-robin of the clusters over (tile pair, k-split) work units (default); opt-in:
+//    cluster-launch-control dynamic scheduling, a stream-K split of the last partial round and
+//    192-column tiles - all three measured, none faster (see the comments at their switches);
 //  * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma
-//    issuer, warps 2..9 = epilogue (two per TMEM lane quadrant, half the tile's columns each);
+//    issuer, warps 2..9 = epilogue (two per TMEM lane quadrant, half the tile's columns each),
+//    warp 10 = tile scheduler of the dynamic mode (idle otherwise);
 //  * operands staged by TMA into a multi-stage SWIZZLE_128B shared-memory ring; both K-major
 //    and MN-major operand layouts are consumed straight from HBM (no transposes for wgrad);
 //  * fp32 accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile i
